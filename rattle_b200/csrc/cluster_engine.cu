@@ -1,0 +1,682 @@
+// Host orchestration of hot path A on one GPU: resident read set, k-mer extraction, and the greedy passes of
+// cluster.cpp:93-259 restated as device-side "waves" (DESIGN.md §2):
+//
+//   cluster_together(i,j,thr) is a pure function, so "read j joins the smallest earlier seed that matches it"
+//   can be evaluated in batches: each wave takes the first W untaken items as candidate seeds, decides which of
+//   them are seeds from their W x W match matrix (phase A), then scores the seeds against every later untaken
+//   item (phase B).  All bookkeeping (selection, resolution, assignment) runs in small kernels; the host only
+//   reads a 4-int status per wave.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "cluster_kernels.cuh"
+#include "common.cuh"
+
+using namespace rtl;
+
+struct EvPool {
+    std::vector<cudaEvent_t> free_, used_[4];
+    double acc[4] = {0, 0, 0, 0};
+    cudaEvent_t get() {
+        cudaEvent_t e;
+        if (!free_.empty()) {
+            e = free_.back();
+            free_.pop_back();
+        } else
+            CK(cudaEventCreate(&e));
+        return e;
+    }
+    void begin(int cat, cudaStream_t s) {
+        cudaEvent_t e = get();
+        CK(cudaEventRecord(e, s));
+        used_[cat].push_back(e);
+    }
+    void end(int cat, cudaStream_t s) { begin(cat, s); }
+    void collect() {  // after a stream sync
+        for (int c = 0; c < 4; ++c) {
+            for (size_t i = 0; i + 1 < used_[c].size(); i += 2) {
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, used_[c][i], used_[c][i + 1]));
+                acc[c] += ms;
+            }
+            for (auto e : used_[c]) free_.push_back(e);
+            used_[c].clear();
+        }
+    }
+    ~EvPool() {
+        for (auto e : free_) cudaEventDestroy(e);
+        for (int c = 0; c < 4; ++c)
+            for (auto e : used_[c]) cudaEventDestroy(e);
+    }
+};
+enum { EV_BV = 0, EV_JOIN = 1, EV_HEAVY = 2, EV_EXTRACT = 3 };
+
+struct ClusterState {
+    uint32_t n = 0;
+    uint64_t total = 0;
+    std::vector<uint64_t> h_off;
+    std::vector<int32_t> h_len;
+    DevBuf<uint8_t> d_bases;
+    DevBuf<uint64_t> d_off;
+    DevBuf<int32_t> d_len;
+    int ex_k = -1, ex_both = -1;
+    DevBuf<uint32_t> kh[2];
+    DevBuf<int32_t> kp[2];
+    DevBuf<uint64_t> bv[2];
+    DevBuf<int32_t> pc;
+    DevBuf<uint32_t> read_list;
+    DevBuf<uint64_t> long_off, long_scratch;
+    // wave state
+    DevBuf<uint8_t> taken, owner_rev, is_seed;
+    DevBuf<int32_t> owner, item_read, cand, seed_item, wave;
+    DevBuf<uint32_t> best, acc;
+    DevBuf<uint16_t> cut;
+    DevBuf<uint64_t> tasks, surv;
+    DevBuf<unsigned long long> counters;  // [0]=n_tasks [1]=n_surv [2]=scratch_cur [3]=pairs
+    DevBuf<int> flags;                    // [0]=input err [1]=overflow
+    DevBuf<unsigned char> scratch;
+    PinBuf<int32_t> h_wave;
+    PinBuf<int> h_flags;
+    PinBuf<unsigned long long> h_counters;
+    EvPool ev;
+    bool smem_attr_set = false;
+};
+
+static ClusterState &state(rtl_ctx *ctx) {
+    if (!ctx->cl) ctx->cl = new ClusterState();
+    return *ctx->cl;
+}
+void cluster_state_free(rtl_ctx *ctx) {
+    delete ctx->cl;
+    ctx->cl = nullptr;
+}
+
+static void set_smem_attrs(ClusterState &S) {
+    if (S.smem_attr_set) return;
+    const int max_smem = 227 * 1024;
+    CK(cudaFuncSetAttribute(k_extract_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CK(cudaFuncSetAttribute(k_bv_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CK(cudaFuncSetAttribute(k_join_count, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CK(cudaFuncSetAttribute(k_pair_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    S.smem_attr_set = true;
+}
+
+// ------------------------------------------------------------------------------------------------ upload
+void cluster_upload(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, uint32_t n) {
+    ClusterState &S = state(ctx);
+    if (n == 0) throw InputError("empty read set");
+    S.n = n;
+    S.total = offsets[n] - offsets[0];
+    S.h_off.resize(n + 1);
+    const uint64_t o0 = offsets[0];
+    for (uint32_t i = 0; i <= n; ++i) S.h_off[i] = offsets[i] - o0;
+    S.h_len.resize(n);
+    for (uint32_t i = 0; i < n; ++i) S.h_len[i] = (int32_t)(S.h_off[i + 1] - S.h_off[i]);
+    CK(cudaMemcpyAsync(S.d_bases.need(S.total + 16), bases + o0, S.total, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(S.d_off.need(n + 1), S.h_off.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    ctx->stats.h2d_bytes += (int64_t)S.total + (int64_t)(n + 1) * 8;
+    S.ex_k = -1;
+    CK(cudaStreamSynchronize(ctx->stream));
+}
+
+// ------------------------------------------------------------------------------------------------ extraction
+static const int SORT_CLASSES[] = {1024, 2048, 4096, 8192, 16384};
+
+void cluster_extract(rtl_ctx *ctx, int k, int both) {
+    ClusterState &S = state(ctx);
+    if (S.n == 0) throw StateError("no reads uploaded");
+    if (k < 1 || k > 16) throw InputError("kmer_size must be in [1,16]");
+    if (S.ex_k == k && S.ex_both == both) return;
+    set_smem_attrs(S);
+    const uint32_t n = S.n;
+    const uint64_t total_k = S.total - (uint64_t)k * n;
+    for (uint32_t i = 0; i < n; ++i)
+        if (S.h_len[i] <= k || S.h_len[i] <= 6) throw InputError("read shorter than or equal to kmer size (kmer.cpp:9)");
+    cudaStream_t st = ctx->stream;
+    S.flags.need(4);
+    CK(cudaMemsetAsync(S.flags.p, 0, 4 * sizeof(int), st));
+    S.d_len.need(n);
+    CK(cudaMemcpyAsync(S.d_len.p, S.h_len.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    ctx->stats.h2d_bytes += (int64_t)n * 4;
+    for (int s = 0; s < 2; ++s) {
+        const bool on = s == 0 || both;
+        S.kh[s].need(on ? total_k + 4 : 4);
+        S.kp[s].need(on ? total_k + 4 : 4);
+        S.bv[s].need(on ? (size_t)n * 64 : 64);
+    }
+    S.pc.need(n);
+    // bucket reads by padded list size
+    const int n_cls = sizeof(SORT_CLASSES) / sizeof(int);
+    std::vector<std::vector<uint32_t>> bucket(n_cls + 1);
+    for (uint32_t i = 0; i < n; ++i) {
+        const int nk = S.h_len[i] - k;
+        int c = 0;
+        while (c < n_cls && nk > SORT_CLASSES[c]) ++c;
+        bucket[c].push_back(i);
+    }
+    std::vector<uint32_t> flat;
+    flat.reserve(n);
+    std::vector<size_t> start(n_cls + 2, 0);
+    for (int c = 0; c <= n_cls; ++c) {
+        start[c] = flat.size();
+        flat.insert(flat.end(), bucket[c].begin(), bucket[c].end());
+    }
+    start[n_cls + 1] = flat.size();
+    S.read_list.need(n);
+    CK(cudaMemcpyAsync(S.read_list.p, flat.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    ctx->stats.h2d_bytes += (int64_t)n * 4;
+    S.ev.begin(EV_EXTRACT, st);
+    for (int c = 0; c < n_cls; ++c) {
+        const size_t cnt = start[c + 1] - start[c];
+        if (!cnt) continue;
+        const int n_pad = SORT_CLASSES[c];
+        const size_t smem = (size_t)n_pad * 8 + 512 + n_pad + 32;
+        const int threads = n_pad <= 2048 ? 256 : (n_pad <= 4096 ? 512 : 1024);
+        // gridDim.x limit is 2^31-1; y = strand
+        dim3 grid((unsigned)cnt, both ? 2 : 1);
+        k_extract_smem<<<grid, threads, smem, st>>>(S.d_bases.p, S.d_off.p, S.read_list.p + start[c], k, n_pad,
+                                                    S.kh[0].p, S.kp[0].p, S.kh[1].p, S.kp[1].p, S.bv[0].p, S.bv[1].p,
+                                                    S.pc.p, S.flags.p);
+        CK(cudaGetLastError());
+        ctx->stats.kernel_launches++;
+    }
+    {
+        const size_t cnt = start[n_cls + 1] - start[n_cls];
+        if (cnt) {
+            std::vector<uint64_t> so(cnt * 2);
+            uint64_t at = 0;
+            for (size_t i = 0; i < cnt; ++i) {
+                int nk = S.h_len[flat[start[n_cls] + i]] - k;
+                uint64_t np = 1;
+                while ((int64_t)np < nk) np <<= 1;
+                so[2 * i] = at;
+                at += np;
+                so[2 * i + 1] = at;
+                at += np;
+            }
+            S.long_off.need(cnt * 2);
+            S.long_scratch.need(at);
+            CK(cudaMemcpyAsync(S.long_off.p, so.data(), cnt * 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+            dim3 grid((unsigned)cnt, both ? 2 : 1);
+            k_extract_long<<<grid, 1024, 0, st>>>(S.d_bases.p, S.d_off.p, S.read_list.p + start[n_cls], S.long_off.p,
+                                                  S.long_scratch.p, k, S.kh[0].p, S.kp[0].p, S.kh[1].p, S.kp[1].p,
+                                                  S.bv[0].p, S.bv[1].p, S.pc.p, S.flags.p);
+            CK(cudaGetLastError());
+            ctx->stats.kernel_launches++;
+            CK(cudaStreamSynchronize(st));  // `so` must outlive the copy
+        }
+    }
+    S.ev.end(EV_EXTRACT, st);
+    int *hf = S.h_flags.need(4);
+    CK(cudaMemcpyAsync(hf, S.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    S.ev.collect();
+    if (hf[0]) throw InputError("base outside ACGTU in input (kmer.hpp:36)");
+    S.ex_k = k;
+    S.ex_both = both;
+}
+
+static ReadView view(ClusterState &S) {
+    ReadView R;
+    R.bases = S.d_bases.p;
+    R.off = S.d_off.p;
+    R.len = S.d_len.p;
+    R.kh[0] = S.kh[0].p;
+    R.kh[1] = S.kh[1].p;
+    R.kp[0] = S.kp[0].p;
+    R.kp[1] = S.kp[1].p;
+    R.bv[0] = S.bv[0].p;
+    R.bv[1] = S.bv[1].p;
+    R.pc = S.pc.p;
+    R.k = S.ex_k;
+    R.n = S.n;
+    return R;
+}
+
+// cluster.cpp:16-19: smallest common count c with double(c)/double(mmax) >= thr, per mmax (exact: same double ops).
+static void make_cut_table(double thr, std::vector<uint16_t> &cut) {
+    cut.assign(4097, 0);
+    if (thr == 0) return;  // `thr == 0 ||` forward, c/mmax >= 0 reverse: everything passes
+    int c = 0;
+    for (int m = 1; m <= 4096; ++m) {
+        while (c <= m && !((double)c / (double)m >= thr)) ++c;
+        cut[m] = (uint16_t)std::min(c, 4097);
+    }
+    cut[0] = 4097;
+}
+
+static const int JC_CAP_W = 4736;   // staged hashes per warp in k_join_count (12 warps x 18.5 KB)
+static const int PH_CAP_C = 1024;   // matches per warp kept in shared memory in k_pair_heavy (8 warps x 20 KB)
+
+// join + heavy over the current task buffer
+static void run_pair_kernels(rtl_ctx *ctx, ClusterState &S, const TaskView &tv, double t_s, double t_v, const Sink &sink,
+                             int64_t *nmatch_out) {
+    cudaStream_t st = ctx->stream;
+    ReadView R = view(S);
+    const int64_t surv_cap = (int64_t)S.surv.cap;
+    S.ev.begin(EV_JOIN, st);
+    k_join_count<<<ctx->n_sm, JC_THREADS, (size_t)(JC_THREADS / 32) * JC_CAP_W * 4, st>>>(
+        tv, S.tasks.p, S.counters.p + 0, R, t_s, JC_CAP_W, S.surv.p, S.counters.p + 1, surv_cap, nmatch_out,
+        S.flags.p + 1, S.counters.p + 4);
+    CK(cudaGetLastError());
+    S.ev.end(EV_JOIN, st);
+    S.ev.begin(EV_HEAVY, st);
+    const size_t smem = (size_t)(PH_THREADS / 32) * heavy_bytes(PH_CAP_C, PH_CAP_C);
+    k_pair_heavy<<<ctx->n_sm * 2, PH_THREADS, smem, st>>>(tv, S.tasks.p, S.surv.p, S.counters.p + 1, surv_cap, R, t_s, t_v,
+                                                          PH_CAP_C, S.scratch.p, S.counters.p + 2,
+                                                          (unsigned long long)S.scratch.cap, sink, S.flags.p + 1,
+                                                          S.counters.p + 5);
+    CK(cudaGetLastError());
+    S.ev.end(EV_HEAVY, st);
+    ctx->stats.kernel_launches += 2;
+}
+
+static void ensure_work_buffers(rtl_ctx *ctx, ClusterState &S, int64_t M) {
+    const int W = ctx->wave;
+    S.taken.need(M);
+    S.owner.need(M);
+    S.owner_rev.need(M);
+    S.best.need(M);
+    S.item_read.need(M);
+    S.cand.need(W);
+    S.seed_item.need(W);
+    S.is_seed.need(W);
+    S.acc.need((size_t)W * W);
+    S.wave.need(4);
+    S.cut.need(4097);
+    S.tasks.need(ctx->task_cap);
+    S.surv.need(ctx->task_cap / 4 + 1024);
+    S.counters.need(8);
+    S.flags.need(4);
+    S.scratch.need((size_t)ctx->scratch_mb << 20);
+    S.h_wave.need(4);
+    S.h_flags.need(4);
+    S.h_counters.need(8);
+}
+
+// One greedy pass (cluster.cpp:124-166 with items = reads, :174-245 with items = cluster representatives).
+// Result: owner[j] = item index of the seed that took item j (owner[j]==j for seeds), owner_rev[j] = rev flag.
+static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, double thr, bool both, double t_s, double t_v,
+                        std::vector<int32_t> &owner, std::vector<uint8_t> &owner_rev) {
+    ClusterState &S = state(ctx);
+    cudaStream_t st = ctx->stream;
+    const int W = ctx->wave;
+    ensure_work_buffers(ctx, S, M);
+    set_smem_attrs(S);
+    const int32_t *d_item_read = nullptr;
+    if (h_item_read) {
+        CK(cudaMemcpyAsync(S.item_read.p, h_item_read, (size_t)M * 4, cudaMemcpyHostToDevice, st));
+        ctx->stats.h2d_bytes += (int64_t)M * 4;
+        d_item_read = S.item_read.p;
+    }
+    std::vector<uint16_t> cut;
+    make_cut_table(thr, cut);
+    CK(cudaMemcpyAsync(S.cut.p, cut.data(), 4097 * 2, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(S.taken.p, 0, M, st));
+    CK(cudaMemsetAsync(S.best.p, 0xff, (size_t)M * 4, st));
+    CK(cudaMemsetAsync(S.owner.p, 0xff, (size_t)M * 4, st));
+    CK(cudaMemsetAsync(S.owner_rev.p, 0, M, st));
+    CK(cudaMemsetAsync(S.wave.p, 0, 16, st));
+    CK(cudaMemsetAsync(S.flags.p, 0, 16, st));
+    CK(cudaStreamSynchronize(st));  // `cut` is pageable host memory
+
+    ReadView R = view(S);
+    int lo = 0;  // host-known lower bound of the device cursor
+    const int64_t chunk = std::max<int64_t>(1024, ctx->task_cap / (2 * (int64_t)W));
+    int32_t *hw = S.h_wave.p;
+    int *hf = S.h_flags.p;
+    while (lo < M) {
+        k_select<<<1, 1024, 0, st>>>(S.taken.p, M, W, S.cand.p, S.wave.p);
+        k_mark_cand<<<4, 256, 0, st>>>(S.taken.p, S.cand.p, S.wave.p, S.owner.p, S.owner_rev.p);
+        CK(cudaMemsetAsync(S.acc.p, 0xff, (size_t)W * W * 4, st));
+        CK(cudaMemsetAsync(S.counters.p, 0, 3 * sizeof(unsigned long long), st));
+        ctx->stats.kernel_launches += 2;
+        // ---- phase A: candidates x candidates
+        {
+            BvScanArgs a{};
+            a.bv_f = S.bv[0].p;
+            a.bv_r = S.bv[1].p;
+            a.pc = S.pc.p;
+            a.item_read = d_item_read;
+            a.seed_item = S.cand.p;
+            a.n_seeds_p = S.wave.p + 1;
+            a.tgt_list = S.cand.p;
+            a.n_tgt_p = S.wave.p + 1;
+            a.t0 = 0;
+            a.t1 = W;
+            a.taken = nullptr;
+            a.cut = S.cut.p;
+            a.both = both;
+            a.order_check = 1;
+            a.rank = ctx->rank;
+            a.world = ctx->world;
+            a.tasks = S.tasks.p;
+            a.n_tasks = S.counters.p;
+            a.task_cap = (int64_t)S.tasks.cap;
+            a.ovf = S.flags.p + 1;
+            a.pair_counter = S.counters.p + 3;
+            dim3 grid((W + 7) / 8, (W + BVS_TS - 1) / BVS_TS);
+            S.ev.begin(EV_BV, st);
+            k_bv_scan<<<grid, BVS_THREADS, BVS_TS * 64 * 8 + BVS_TS * 8, st>>>(a);
+            CK(cudaGetLastError());
+            S.ev.end(EV_BV, st);
+            ctx->stats.kernel_launches++;
+            ctx->stats.bv_launches++;
+            TaskView tv{S.cand.p, S.cand.p, d_item_read};
+            Sink sink{};
+            sink.mode = 1;
+            sink.acc = S.acc.p;
+            sink.W = W;
+            run_pair_kernels(ctx, S, tv, t_s, t_v, sink, nullptr);
+            if (ctx->world > 1 && ctx->allreduce(ctx->allreduce_user, S.acc.p, (int64_t)W * W) != 0)
+                throw CudaError("allreduce callback failed");
+            k_resolve<<<1, 32, 0, st>>>(S.acc.p, W, S.cand.p, S.wave.p, S.seed_item.p, S.is_seed.p, S.owner.p,
+                                        S.owner_rev.p);
+            ctx->stats.kernel_launches++;
+        }
+        // ---- phase B: seeds x every later untaken item (items below the cursor are all taken)
+        const int b_lo = lo;
+        for (int64_t c0 = b_lo; c0 < M; c0 += chunk) {
+            const int64_t c1 = std::min<int64_t>(M, c0 + chunk);
+            CK(cudaMemsetAsync(S.counters.p, 0, 3 * sizeof(unsigned long long), st));
+            BvScanArgs a{};
+            a.bv_f = S.bv[0].p;
+            a.bv_r = S.bv[1].p;
+            a.pc = S.pc.p;
+            a.item_read = d_item_read;
+            a.seed_item = S.seed_item.p;
+            a.n_seeds_p = S.wave.p + 2;
+            a.tgt_list = nullptr;
+            a.t0 = (int32_t)c0;
+            a.t1 = (int32_t)c1;
+            a.taken = S.taken.p;
+            a.cut = S.cut.p;
+            a.both = both;
+            a.order_check = 0;
+            a.rank = ctx->rank;
+            a.world = ctx->world;
+            a.tasks = S.tasks.p;
+            a.n_tasks = S.counters.p;
+            a.task_cap = (int64_t)S.tasks.cap;
+            a.ovf = S.flags.p + 1;
+            a.pair_counter = S.counters.p + 3;
+            const int64_t nt = c1 - c0;
+            int gx = (int)std::min<int64_t>((nt + 7) / 8, (int64_t)ctx->n_sm * 8);
+            dim3 grid(gx, (W + BVS_TS - 1) / BVS_TS);
+            S.ev.begin(EV_BV, st);
+            k_bv_scan<<<grid, BVS_THREADS, BVS_TS * 64 * 8 + BVS_TS * 8, st>>>(a);
+            CK(cudaGetLastError());
+            S.ev.end(EV_BV, st);
+            ctx->stats.kernel_launches++;
+            ctx->stats.bv_launches++;
+            TaskView tv{S.seed_item.p, nullptr, d_item_read};
+            Sink sink{};
+            sink.mode = 2;
+            sink.best = S.best.p;
+            run_pair_kernels(ctx, S, tv, t_s, t_v, sink, nullptr);
+        }
+        if (b_lo < M) {
+            if (ctx->world > 1 && ctx->allreduce(ctx->allreduce_user, S.best.p + b_lo, (int64_t)(M - b_lo)) != 0)
+                throw CudaError("allreduce callback failed");
+            k_apply<<<ctx->n_sm, 256, 0, st>>>(S.best.p, b_lo, M, S.seed_item.p, S.taken.p, S.owner.p, S.owner_rev.p);
+            ctx->stats.kernel_launches++;
+        }
+        CK(cudaMemcpyAsync(hw, S.wave.p, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hf, S.flags.p, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->stats.d2h_bytes += 32;
+        S.ev.collect();
+        ctx->stats.waves++;
+        if (hf[1]) {
+            if (hf[1] == 3) throw CapacityError("match scratch exhausted: raise option scratch_mb");
+            throw CapacityError("candidate-pair buffer exhausted: raise option task_cap");
+        }
+        lo = hw[0];
+    }
+    owner.resize(M);
+    owner_rev.resize(M);
+    CK(cudaMemcpyAsync(owner.data(), S.owner.p, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(owner_rev.data(), S.owner_rev.p, M, cudaMemcpyDeviceToHost, st));
+    unsigned long long *hc = S.h_counters.p;
+    CK(cudaMemcpyAsync(hc, S.counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->stats.d2h_bytes += (int64_t)M * 5;
+    ctx->stats.rounds++;
+    (void)R;
+}
+
+// ------------------------------------------------------------------------------------------------ cluster_reads
+struct Member {
+    int32_t id;
+    uint8_t rev;
+};
+struct Cluster {
+    Member main;
+    std::vector<Member> mem;
+};
+
+// cluster.cpp:67-91 (sorts the member vector in place; that order is what clusters.out stores)
+static Member pick_main(std::vector<Member> &m, const std::vector<int32_t> &len, double pct) {
+    const Member old = m[0];
+    std::stable_sort(m.begin(), m.end(), [](const Member &a, const Member &b) { return a.id > b.id; });
+    std::stable_sort(m.begin(), m.end(), [&len](const Member &a, const Member &b) { return len[a.id] > len[b.id]; });
+    int nsid = (int)(m.size() * pct);
+    Member ns = m[nsid];
+    while (ns.rev != old.rev && (size_t)nsid < m.size() - 1) ns = m[++nsid];
+    if ((size_t)nsid == m.size() - 1) return old;
+    return ns;
+}
+
+void cluster_run(rtl_ctx *ctx, int k, double t_s, double t_v, double bv_thr, double bv_min, double bv_falloff,
+                 double repr_pct, int is_rna, int32_t *main_id, uint8_t *main_rev, int64_t *cl_off, int32_t *mem_id,
+                 uint8_t *mem_rev, int32_t *n_clusters) {
+    ClusterState &S = state(ctx);
+    const double t_begin = now_ms();
+    const bool both = !is_rna;
+    for (int c = 0; c < 4; ++c) S.ev.acc[c] = 0;
+    cluster_extract(ctx, k, both);
+    const int N = (int)S.n;
+    ensure_work_buffers(ctx, S, N);
+    CK(cudaMemsetAsync(S.counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+
+    std::vector<int32_t> owner;
+    std::vector<uint8_t> orev;
+    greedy_pass(ctx, N, nullptr, bv_thr, both, t_s, t_v, owner, orev);
+
+    std::vector<Cluster> cl;
+    {
+        std::vector<int32_t> slot(N, -1);
+        for (int i = 0; i < N; ++i)
+            if (owner[i] == i) {
+                slot[i] = (int32_t)cl.size();
+                cl.emplace_back();
+                cl.back().mem.push_back(Member{i, 0});
+            }
+        for (int i = 0; i < N; ++i)
+            if (owner[i] != i) cl[slot[owner[i]]].mem.push_back(Member{i, orev[i]});
+        for (auto &c : cl) c.main = pick_main(c.mem, S.h_len, repr_pct);
+    }
+
+    double thr = bv_thr - bv_falloff;
+    bool last = false;
+    std::vector<int32_t> rep;
+    while (thr >= bv_min || last) {
+        const int M = (int)cl.size();
+        rep.resize(M);
+        for (int i = 0; i < M; ++i) rep[i] = cl[i].main.id;
+        greedy_pass(ctx, M, rep.data(), thr, both, t_s, t_v, owner, orev);
+        std::vector<Cluster> next;
+        std::vector<int32_t> slot(M, -1);
+        for (int i = 0; i < M; ++i)
+            if (owner[i] == i) {
+                slot[i] = (int32_t)next.size();
+                next.emplace_back();
+                next.back().mem = cl[i].mem;
+            }
+        for (int i = 0; i < M; ++i)
+            if (owner[i] != i) {
+                auto &dst = next[slot[owner[i]]].mem;
+                for (Member s : cl[i].mem) {
+                    if (orev[i]) s.rev = !s.rev;  // cluster.cpp:232-234
+                    dst.push_back(s);
+                }
+            }
+        for (auto &c : next) c.main = pick_main(c.mem, S.h_len, repr_pct);
+        cl.swap(next);
+        if (last) break;
+        thr -= bv_falloff;
+        if (thr < bv_min && !last) {
+            last = true;
+            thr = 0.0;
+        }
+    }
+
+    int64_t o = 0;
+    for (size_t c = 0; c < cl.size(); ++c) {
+        main_id[c] = cl[c].main.id;
+        main_rev[c] = cl[c].main.rev;
+        cl_off[c] = o;
+        for (auto &m : cl[c].mem) {
+            mem_id[o] = m.id;
+            mem_rev[o] = m.rev;
+            ++o;
+        }
+    }
+    cl_off[cl.size()] = o;
+    *n_clusters = (int32_t)cl.size();
+    ctx->stats.bv_pairs += (int64_t)S.h_counters.p[3];  // device counters are cumulative over the passes
+    ctx->stats.full_pairs += (int64_t)S.h_counters.p[4];
+    ctx->stats.heavy_pairs += (int64_t)S.h_counters.p[5];
+    ctx->stats.bv_ms += S.ev.acc[EV_BV];
+    ctx->stats.join_ms += S.ev.acc[EV_JOIN];
+    ctx->stats.heavy_ms += S.ev.acc[EV_HEAVY];
+    ctx->stats.extract_ms += S.ev.acc[EV_EXTRACT];
+    ctx->stats.total_ms += now_ms() - t_begin;
+}
+
+// ------------------------------------------------------------------------------------------------ function-level entry points
+void cluster_download_kmers(rtl_ctx *ctx, uint32_t *fh, int32_t *fp, uint32_t *rh, int32_t *rp, uint64_t *bf,
+                            uint64_t *br) {
+    ClusterState &S = state(ctx);
+    const uint64_t total_k = S.total - (uint64_t)S.ex_k * S.n;
+    cudaStream_t st = ctx->stream;
+    if (fh) CK(cudaMemcpyAsync(fh, S.kh[0].p, total_k * 4, cudaMemcpyDeviceToHost, st));
+    if (fp) CK(cudaMemcpyAsync(fp, S.kp[0].p, total_k * 4, cudaMemcpyDeviceToHost, st));
+    if (S.ex_both) {
+        if (rh) CK(cudaMemcpyAsync(rh, S.kh[1].p, total_k * 4, cudaMemcpyDeviceToHost, st));
+        if (rp) CK(cudaMemcpyAsync(rp, S.kp[1].p, total_k * 4, cudaMemcpyDeviceToHost, st));
+        if (br) CK(cudaMemcpyAsync(br, S.bv[1].p, (size_t)S.n * 512, cudaMemcpyDeviceToHost, st));
+    } else if (br)
+        memset(br, 0, (size_t)S.n * 512);
+    if (bf) CK(cudaMemcpyAsync(bf, S.bv[0].p, (size_t)S.n * 512, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+}
+
+void cluster_bv_scan_dense(rtl_ctx *ctx, int k, int is_rna, const int32_t *seed_reads, int n_seeds,
+                           const int32_t *target_reads, int n_targets, double thr, uint32_t *common, uint8_t *pass) {
+    ClusterState &S = state(ctx);
+    cluster_extract(ctx, k, !is_rna);
+    set_smem_attrs(S);
+    cudaStream_t st = ctx->stream;
+    DevBuf<int32_t> d_seeds, d_tg, d_ns;
+    DevBuf<uint32_t> d_common;
+    DevBuf<uint8_t> d_pass;
+    DevBuf<uint16_t> d_cut;
+    DevBuf<unsigned long long> d_cnt;
+    DevBuf<int> d_ovf;
+    const size_t np = (size_t)n_seeds * n_targets;
+    std::vector<uint16_t> cut;
+    make_cut_table(thr, cut);
+    CK(cudaMemcpyAsync(d_seeds.need(n_seeds), seed_reads, (size_t)n_seeds * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_tg.need(n_targets), target_reads, (size_t)n_targets * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_ns.need(1), &n_seeds, 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_cut.need(4097), cut.data(), 4097 * 2, cudaMemcpyHostToDevice, st));
+    d_common.need(np);
+    d_pass.need(np);
+    CK(cudaMemsetAsync(d_cnt.need(2), 0, 16, st));
+    CK(cudaMemsetAsync(d_ovf.need(1), 0, 4, st));
+    BvScanArgs a{};
+    a.bv_f = S.bv[0].p;
+    a.bv_r = S.bv[1].p;
+    a.pc = S.pc.p;
+    a.item_read = nullptr;
+    a.seed_item = d_seeds.p;
+    a.n_seeds_p = d_ns.p;
+    a.tgt_list = d_tg.p;
+    a.n_tgt_p = nullptr;
+    a.t0 = 0;
+    a.t1 = n_targets;
+    a.cut = d_cut.p;
+    a.both = !is_rna;
+    a.order_check = 0;
+    a.rank = 0;
+    a.world = 1;
+    a.tasks = nullptr;
+    a.n_tasks = d_cnt.p;
+    a.ovf = d_ovf.p;
+    a.dense_common = d_common.p;
+    a.dense_pass = d_pass.p;
+    a.pair_counter = d_cnt.p + 1;
+    int gx = (int)std::min<int64_t>(((int64_t)n_targets + 7) / 8, (int64_t)ctx->n_sm * 8);
+    dim3 grid(std::max(gx, 1), (n_seeds + BVS_TS - 1) / BVS_TS);
+    k_bv_scan<<<grid, BVS_THREADS, BVS_TS * 64 * 8 + BVS_TS * 8, st>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(common, d_common.p, np * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pass, d_pass.p, np, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+}
+
+void cluster_pair_similarity(rtl_ctx *ctx, int k, int is_rna, const int32_t *a_read, const int32_t *b_read,
+                             const uint8_t *strand, int64_t n_tasks, double t_s, double t_v, int64_t *n_common,
+                             int32_t *bases, int32_t *n_dist, double *var, uint8_t *accept) {
+    ClusterState &S = state(ctx);
+    cluster_extract(ctx, k, !is_rna);
+    set_smem_attrs(S);
+    cudaStream_t st = ctx->stream;
+    if (n_tasks >= (1ll << 31)) throw CapacityError("too many tasks");
+    std::vector<uint64_t> tasks(n_tasks);
+    for (int64_t i = 0; i < n_tasks; ++i) {
+        if (strand[i] && is_rna) throw InputError("reverse-strand task on an RNA (forward-only) extraction");
+        tasks[i] = make_task((uint32_t)i, strand[i], (uint32_t)i);
+    }
+    DevBuf<int32_t> d_a, d_b, d_bases, d_nd;
+    DevBuf<int64_t> d_nm;
+    DevBuf<double> d_var;
+    DevBuf<uint8_t> d_acc;
+    S.tasks.need(std::max<int64_t>(n_tasks, 1));
+    S.surv.need(std::max<int64_t>(n_tasks, 1));
+    S.counters.need(8);
+    S.flags.need(4);
+    S.scratch.need((size_t)ctx->scratch_mb << 20);
+    CK(cudaMemcpyAsync(S.tasks.p, tasks.data(), n_tasks * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_a.need(n_tasks), a_read, n_tasks * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_b.need(n_tasks), b_read, n_tasks * 4, cudaMemcpyHostToDevice, st));
+    unsigned long long cnt[4] = {(unsigned long long)n_tasks, 0, 0, 0};
+    CK(cudaMemcpyAsync(S.counters.p, cnt, sizeof(cnt), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(S.flags.p, 0, 16, st));
+    CK(cudaMemsetAsync(d_bases.need(n_tasks), 0xff, n_tasks * 4, st));
+    CK(cudaMemsetAsync(d_nd.need(n_tasks), 0, n_tasks * 4, st));
+    CK(cudaMemsetAsync(d_var.need(n_tasks), 0, n_tasks * 8, st));
+    CK(cudaMemsetAsync(d_acc.need(n_tasks), 0, n_tasks, st));
+    d_nm.need(n_tasks);
+    TaskView tv{d_a.p, d_b.p, nullptr};
+    Sink sink{};
+    sink.mode = 0;
+    sink.bases = d_bases.p;
+    sink.n_dist = d_nd.p;
+    sink.var = d_var.p;
+    sink.accept = d_acc.p;
+    run_pair_kernels(ctx, S, tv, t_s, t_v, sink, d_nm.p);
+    int hf[4];
+    CK(cudaMemcpyAsync(hf, S.flags.p, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(n_common, d_nm.p, n_tasks * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(bases, d_bases.p, n_tasks * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(n_dist, d_nd.p, n_tasks * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(var, d_var.p, n_tasks * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(accept, d_acc.p, n_tasks, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    S.ev.collect();
+    if (hf[1]) throw CapacityError("scratch or survivor buffer exhausted in pair_similarity");
+}

@@ -1,0 +1,730 @@
+// sm_100a kernels of hot path A (greedy k-mer/bitvector clustering).  No tensor-core use: every kernel here is
+// integer/byte work bounded by HBM bandwidth, POPC issue or shared-memory latency.
+//
+//   k_extract_*     kmer.cpp:6-42       k-mer (hash,pos) lists sorted by (hash,pos) + 4096-bit 6-mer bitvectors
+//   k_bv_scan       cluster.cpp:13-19,43 bitvector AND+popcount filter, seeds tiled in shared memory
+//   k_join_count    kmer.cpp:45-67      size of the sorted-list multiset join (and the exact reject bound)
+//   k_pair_heavy    kmer.cpp:45-67 + similarity.cpp:4-97 + utils.cpp:36-55 + cluster.cpp:24-37
+//   k_select / k_resolve / k_apply      the greedy bookkeeping of cluster.cpp:124-166,171-245, batched in waves
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rtl {
+
+// device view of the resident read set
+struct ReadView {
+    const uint8_t *bases;
+    const uint64_t *off;   // n+1
+    const int32_t *len;    // n
+    const uint32_t *kh[2]; // sorted k-mer hashes, forward / reverse-complement strand
+    const int32_t *kp[2];  // positions
+    const uint64_t *bv[2]; // n x 64
+    const int32_t *pc;     // popcount of bv[0]
+    int k;
+    uint32_t n;
+    __device__ __forceinline__ uint64_t koff(uint32_t r) const { return off[r] - (uint64_t)k * r; }
+};
+
+// A/C/T(U)/G -> 0/1/2/3 (kmer.hpp:25-31): bits 1..2 of the ASCII code give exactly that order.
+__device__ __forceinline__ int base_code(uint8_t c) {
+    bool ok = (c == 'A') | (c == 'C') | (c == 'G') | (c == 'T') | (c == 'U');
+    return ok ? ((c >> 1) & 3) : -1;
+}
+
+// ------------------------------------------------------------------------------------------------ K2: extraction
+// One CTA per (read, strand).  Keys (hash<<32 | pos) are bitonic-sorted in shared memory.
+// smem: keys[n_pad] u64 | bvw[128] u32 | codes[n_pad+32] u8
+__global__ void k_extract_smem(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ off,
+                               const uint32_t *__restrict__ read_list, int k, int n_pad, uint32_t *kh_f, int32_t *kp_f,
+                               uint32_t *kh_r, int32_t *kp_r, uint64_t *bv_f, uint64_t *bv_r, int32_t *pc, int *err) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint64_t *keys = (uint64_t *)sm_raw;
+    uint32_t *bvw = (uint32_t *)(keys + n_pad);
+    uint8_t *codes = (uint8_t *)(bvw + 128);
+    const uint32_t r = read_list[blockIdx.x];
+    const int strand = blockIdx.y;
+    const uint64_t o = off[r];
+    const int len = (int)(off[r + 1] - o);
+    const int n = len - k;
+    const int tid = threadIdx.x, nt = blockDim.x;
+
+    for (int p = tid; p < len; p += nt) {
+        int c = strand == 0 ? base_code(bases[o + p]) : base_code(bases[o + (len - 1 - p)]);
+        if (c < 0) {
+            atomicExch(err, 2);
+            c = 0;
+        } else if (strand)
+            c ^= 2;  // complement: A<->T, C<->G  (utils.cpp:15-24)
+        codes[p] = (uint8_t)c;
+    }
+    if (tid < 128) bvw[tid] = 0;
+    __syncthreads();
+    for (int p = tid; p < n_pad; p += nt) {
+        uint64_t key = ~0ull;
+        if (p < n) {
+            uint32_t h = 0;
+            for (int i = 0; i < k; ++i) h = (h << 2) | codes[p + i];
+            key = ((uint64_t)h << 32) | (uint32_t)p;
+        }
+        keys[p] = key;
+    }
+    for (int p = tid; p < len - 6; p += nt) {  // 6-mers at pos 0..len-7 (kmer.cpp:28)
+        uint32_t h = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) h = (h << 2) | codes[p + i];
+        atomicOr(&bvw[h >> 5], 1u << (h & 31));
+    }
+    // bitonic sort, ascending
+    for (int size = 2; size <= n_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = tid; t < (n_pad >> 1); t += nt) {
+                int i = 2 * t - (t & (stride - 1));
+                int j = i + stride;
+                uint64_t a = keys[i], b = keys[j];
+                bool asc = (i & size) == 0;
+                if ((a > b) == asc) {
+                    keys[i] = b;
+                    keys[j] = a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const uint64_t ko = o - (uint64_t)k * r;
+    uint32_t *kh = strand ? kh_r : kh_f;
+    int32_t *kp = strand ? kp_r : kp_f;
+    for (int p = tid; p < n; p += nt) {
+        uint64_t key = keys[p];
+        kh[ko + p] = (uint32_t)(key >> 32);
+        kp[ko + p] = (int32_t)(uint32_t)key;
+    }
+    uint64_t *bv = strand ? bv_r : bv_f;
+    if (tid < 64) bv[(uint64_t)r * 64 + tid] = (uint64_t)bvw[2 * tid] | ((uint64_t)bvw[2 * tid + 1] << 32);
+    if (strand == 0 && tid < 32) {
+        int c = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) c += __popc(bvw[tid * 4 + w]);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+        if (tid == 0) pc[r] = c;
+    }
+}
+
+// Same, for reads whose key list does not fit shared memory: keys live in a global scratch segment.
+__global__ void k_extract_long(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ off,
+                               const uint32_t *__restrict__ read_list, const uint64_t *__restrict__ scratch_off,
+                               uint64_t *scratch, int k, uint32_t *kh_f, int32_t *kp_f, uint32_t *kh_r, int32_t *kp_r,
+                               uint64_t *bv_f, uint64_t *bv_r, int32_t *pc, int *err) {
+    __shared__ uint32_t bvw[128];
+    const uint32_t r = read_list[blockIdx.x];
+    const int strand = blockIdx.y;
+    const uint64_t o = off[r];
+    const int len = (int)(off[r + 1] - o);
+    const int n = len - k;
+    int n_pad = 1;
+    while (n_pad < n) n_pad <<= 1;
+    uint64_t *keys = scratch + scratch_off[blockIdx.x * 2 + strand];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    auto code_at = [&](int p) -> int {
+        int c = strand == 0 ? base_code(bases[o + p]) : base_code(bases[o + (len - 1 - p)]);
+        if (c < 0) {
+            atomicExch(err, 2);
+            return 0;
+        }
+        return strand ? (c ^ 2) : c;
+    };
+    if (tid < 128) bvw[tid] = 0;
+    __syncthreads();
+    for (int p = tid; p < n_pad; p += nt) {
+        uint64_t key = ~0ull;
+        if (p < n) {
+            uint32_t h = 0;
+            for (int i = 0; i < k; ++i) h = (h << 2) | (uint32_t)code_at(p + i);
+            key = ((uint64_t)h << 32) | (uint32_t)p;
+        }
+        keys[p] = key;
+    }
+    for (int p = tid; p < len - 6; p += nt) {
+        uint32_t h = 0;
+        for (int i = 0; i < 6; ++i) h = (h << 2) | (uint32_t)code_at(p + i);
+        atomicOr(&bvw[h >> 5], 1u << (h & 31));
+    }
+    for (int size = 2; size <= n_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = tid; t < (n_pad >> 1); t += nt) {
+                int i = 2 * t - (t & (stride - 1));
+                int j = i + stride;
+                uint64_t a = keys[i], b = keys[j];
+                bool asc = (i & size) == 0;
+                if ((a > b) == asc) {
+                    keys[i] = b;
+                    keys[j] = a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const uint64_t ko = o - (uint64_t)k * r;
+    uint32_t *kh = strand ? kh_r : kh_f;
+    int32_t *kp = strand ? kp_r : kp_f;
+    for (int p = tid; p < n; p += nt) {
+        uint64_t key = keys[p];
+        kh[ko + p] = (uint32_t)(key >> 32);
+        kp[ko + p] = (int32_t)(uint32_t)key;
+    }
+    uint64_t *bv = strand ? bv_r : bv_f;
+    if (tid < 64) bv[(uint64_t)r * 64 + tid] = (uint64_t)bvw[2 * tid] | ((uint64_t)bvw[2 * tid + 1] << 32);
+    if (strand == 0 && tid < 32) {
+        int c = 0;
+        for (int w = 0; w < 4; ++w) c += __popc(bvw[tid * 4 + w]);
+        for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+        if (tid == 0) pc[r] = c;
+    }
+}
+
+__global__ void k_lengths(const uint64_t *__restrict__ off, int32_t *len, uint32_t n, int k, int *err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        int l = (int)(off[i + 1] - off[i]);
+        len[i] = l;
+        if (l <= k || l <= 6) atomicExch(err, 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tasks
+// task = t (bits 0..31) | strand (bit 32) | s (bits 33..63)
+//   s indexes `seed_item` (or is the item itself), t indexes `tgt_list` (or is the item itself);
+//   items map to reads through `item_read` (or are reads themselves).
+struct TaskView {
+    const int32_t *seed_item;
+    const int32_t *tgt_list;
+    const int32_t *item_read;
+    __device__ __forceinline__ void decode(uint64_t task, uint32_t &a_read, uint32_t &b_read, int &strand) const {
+        uint32_t t = (uint32_t)task;
+        strand = (int)((task >> 32) & 1);
+        uint32_t s = (uint32_t)(task >> 33);
+        uint32_t ai = seed_item ? (uint32_t)seed_item[s] : s;
+        uint32_t bi = tgt_list ? (uint32_t)tgt_list[t] : t;
+        a_read = item_read ? (uint32_t)item_read[ai] : ai;
+        b_read = item_read ? (uint32_t)item_read[bi] : bi;
+    }
+};
+__host__ __device__ __forceinline__ uint64_t make_task(uint32_t s, int strand, uint32_t t) {
+    return ((uint64_t)s << 33) | ((uint64_t)(strand & 1) << 32) | t;
+}
+
+// ------------------------------------------------------------------------------------------------ K3: bitvector scan
+// grid.x strides over targets (one warp per target), grid.y = seed tiles of `TS` seeds staged in shared memory.
+// Each lane owns two 64-bit words of the target's forward and reverse bitvector (one coalesced uint4 load each);
+// per seed: LDS.128 of the seed words, AND, POPC, 5-step butterfly; 32 seeds are evaluated per threshold/ballot step.
+// Emits (seed slot, target, strand) tasks for pairs that pass cluster.cpp:19 / :43, or dense results for tests.
+constexpr int BVS_TS = 128;       // seeds per shared-memory tile (64 KB)
+constexpr int BVS_THREADS = 256;  // 8 warps
+struct BvScanArgs {
+    const uint64_t *bv_f, *bv_r;
+    const int32_t *pc;
+    const int32_t *item_read;  // nullable
+    const int32_t *seed_item;  // n_seeds (device count in *n_seeds_p)
+    const int32_t *n_seeds_p;
+    const int32_t *tgt_list;   // nullable: explicit target items
+    const int32_t *n_tgt_p;    // nullable: device count for tgt_list
+    int32_t t0, t1;            // target range when tgt_list == nullptr (t1 also caps the list)
+    const uint8_t *taken;      // nullable
+    const uint16_t *cut;       // 4097 entries: min common count that passes at mmax
+    int both;                  // reverse strand evaluated
+    int order_check;           // require seed item < target item
+    int rank, world;           // target sharding
+    uint64_t *tasks;
+    unsigned long long *n_tasks;
+    int64_t task_cap;
+    int *ovf;
+    uint32_t *dense_common;    // nullable (tests): [n_seeds x n_targets]
+    uint8_t *dense_pass;
+    unsigned long long *pair_counter;  // evaluated pairs
+};
+
+__global__ void __launch_bounds__(BVS_THREADS) k_bv_scan(BvScanArgs A) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint64_t *sseed = (uint64_t *)sm_raw;                 // [TS][64]
+    int32_t *sitem = (int32_t *)(sseed + BVS_TS * 64);    // [TS]
+    int32_t *spc = sitem + BVS_TS;                        // [TS]
+    const int n_seeds = *A.n_seeds_p;
+    const int s0 = blockIdx.y * BVS_TS;
+    if (s0 >= n_seeds) return;
+    const int ts = min(BVS_TS, n_seeds - s0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < ts * 64; i += BVS_THREADS) {
+        int s = i >> 6;
+        int it = A.seed_item[s0 + s];
+        uint32_t rd = A.item_read ? (uint32_t)A.item_read[it] : (uint32_t)it;
+        sseed[i] = A.bv_f[(uint64_t)rd * 64 + (i & 63)];
+    }
+    for (int s = tid; s < ts; s += BVS_THREADS) {
+        int it = A.seed_item[s0 + s];
+        uint32_t rd = A.item_read ? (uint32_t)A.item_read[it] : (uint32_t)it;
+        sitem[s] = it;
+        spc[s] = A.pc[rd];
+    }
+    __syncthreads();
+    int n_t = A.tgt_list ? (A.n_tgt_p ? *A.n_tgt_p : A.t1) : (A.t1 - A.t0);
+    unsigned long long my_pairs = 0;
+    for (int x = blockIdx.x * (BVS_THREADS / 32) + warp; x < n_t; x += gridDim.x * (BVS_THREADS / 32)) {
+        const int tslot = A.tgt_list ? x : A.t0 + x;  // value stored in the task
+        const int item = A.tgt_list ? A.tgt_list[x] : tslot;
+        if (A.world > 1 && (item % A.world) != A.rank) continue;
+        if (A.taken && A.taken[item]) continue;
+        const uint32_t rd = A.item_read ? (uint32_t)A.item_read[item] : (uint32_t)item;
+        const ulonglong2 f = *reinterpret_cast<const ulonglong2 *>(A.bv_f + (uint64_t)rd * 64 + 2 * lane);
+        ulonglong2 rv = make_ulonglong2(0, 0);
+        if (A.both) rv = *reinterpret_cast<const ulonglong2 *>(A.bv_r + (uint64_t)rd * 64 + 2 * lane);
+        const int pcj = A.pc[rd];
+        for (int g = 0; g < ts; g += 32) {
+            uint32_t mine = 0;
+            const int lim = min(32, ts - g);
+            for (int q = 0; q < lim; ++q) {
+                const ulonglong2 sw = *reinterpret_cast<const ulonglong2 *>(sseed + (g + q) * 64 + 2 * lane);
+                uint32_t c = (uint32_t)(__popcll(sw.x & f.x) + __popcll(sw.y & f.y));
+                c |= (uint32_t)(__popcll(sw.x & rv.x) + __popcll(sw.y & rv.y)) << 16;
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) c += __shfl_xor_sync(0xffffffffu, c, sft);
+                if (lane == q) mine = c;
+            }
+            const int s = g + lane;
+            bool valid = lane < lim;
+            if (valid && A.order_check) valid = sitem[s] < item;
+            const uint32_t cf = mine & 0xffffu, cr = mine >> 16;
+            bool pf = false, pr = false;
+            if (valid) {
+                const int mmax = max(spc[s], pcj);
+                const uint32_t cutv = A.cut[mmax];
+                pf = cf >= cutv;
+                pr = A.both && cr >= cutv;
+            }
+            my_pairs += (unsigned long long)__popc(__ballot_sync(0xffffffffu, valid));
+            if (A.dense_common) {
+                if (lane < lim) {
+                    size_t idx = (size_t)(s0 + s) * (size_t)n_t + (size_t)x;
+                    A.dense_common[idx] = mine;
+                    A.dense_pass[idx] = (uint8_t)((pf ? 1 : 0) | (pr ? 2 : 0));
+                }
+            }
+            if (A.tasks) {
+                const uint32_t mf = __ballot_sync(0xffffffffu, pf), mr = __ballot_sync(0xffffffffu, pr);
+                const int tot = __popc(mf) + __popc(mr);
+                if (tot) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(A.n_tasks, (unsigned long long)tot);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base + tot > (unsigned long long)A.task_cap) {
+                        if (lane == 0) atomicExch(A.ovf, 1);
+                    } else {
+                        const uint32_t below = (1u << lane) - 1u;
+                        if (pf) A.tasks[base + __popc(mf & below)] = make_task((uint32_t)(s0 + s), 0, (uint32_t)tslot);
+                        if (pr)
+                            A.tasks[base + __popc(mf) + __popc(mr & below)] =
+                                make_task((uint32_t)(s0 + s), 1, (uint32_t)tslot);
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0 && my_pairs && A.pair_counter) atomicAdd(A.pair_counter, my_pairs);
+}
+
+// ------------------------------------------------------------------------------------------------ K4: list join
+__device__ __forceinline__ int lower_bound_u32(const uint32_t *p, int n, uint32_t v) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (p[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// Lane-local part of get_common_kmers (kmer.cpp:45-67): A positions [a0,a1) against all of B.
+// EMIT=false: returns the number of cross pairs.  EMIT=true: also writes (posA<<32|posB) keys from out[0].
+template <bool EMIT>
+__device__ __forceinline__ long long join_range(const uint32_t *pa, const uint32_t *pb, int a0, int a1, int n2,
+                                                const int32_t *posa, const int32_t *posb, uint64_t *out) {
+    long long cnt = 0;
+    if (a0 >= a1) return 0;
+    int y = lower_bound_u32(pb, n2, pa[a0]);
+    int ye = y;
+    uint32_t hprev = 0;
+    bool have = false;
+    for (int x = a0; x < a1; ++x) {
+        const uint32_t h = pa[x];
+        if (!(have && h == hprev)) {
+            y = ye;
+            while (y < n2 && pb[y] < h) ++y;
+            ye = y;
+            while (ye < n2 && pb[ye] == h) ++ye;
+            hprev = h;
+            have = true;
+        }
+        if (EMIT) {
+            const uint64_t hi = (uint64_t)(uint32_t)posa[x] << 32;
+            for (int z = y; z < ye; ++z) out[cnt + (z - y)] = hi | (uint32_t)posb[z];
+        }
+        cnt += ye - y;
+    }
+    return cnt;
+}
+
+// warp per task; survivors of the exact bound  k*n_common/min_len >= t_s  are appended to `surv`
+// as (task index | min(n_common, 2^32-1) << 32).
+constexpr int JC_THREADS = 384;  // 12 warps x 18.5 KB of staged hash lists
+__global__ void __launch_bounds__(JC_THREADS) k_join_count(TaskView tv, const uint64_t *__restrict__ tasks,
+                                                           const unsigned long long *n_tasks_p, ReadView R, double t_s,
+                                                           int cap_w, uint64_t *surv, unsigned long long *n_surv,
+                                                           int64_t surv_cap, int64_t *nmatch_out, int *ovf,
+                                                           unsigned long long *stat_full) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *sw = (uint32_t *)sm_raw + (size_t)warp * cap_w;
+    const unsigned long long n_tasks = *n_tasks_p;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && stat_full) atomicAdd(stat_full, n_tasks);
+    const unsigned long long wstride = (unsigned long long)gridDim.x * (JC_THREADS / 32);
+    for (unsigned long long ti = (unsigned long long)blockIdx.x * (JC_THREADS / 32) + warp; ti < n_tasks; ti += wstride) {
+        uint32_t ar, br;
+        int strand;
+        tv.decode(tasks[ti], ar, br, strand);
+        const int la = R.len[ar], lb = R.len[br];
+        const int n1 = la - R.k, n2 = lb - R.k;
+        const uint32_t *A = R.kh[0] + R.koff(ar);
+        const uint32_t *B = (strand ? R.kh[1] : R.kh[0]) + R.koff(br);
+        const uint32_t *pa = A, *pb = B;
+        if (n1 + n2 <= cap_w) {
+            for (int i = lane; i < n1; i += 32) sw[i] = A[i];
+            for (int i = lane; i < n2; i += 32) sw[n1 + i] = B[i];
+            __syncwarp();
+            pa = sw;
+            pb = sw + n1;
+        }
+        const int per = (n1 + 31) >> 5;
+        const int a0 = min(n1, lane * per), a1 = min(n1, a0 + per);
+        long long cnt = join_range<false>(pa, pb, a0, a1, n2, nullptr, nullptr, nullptr);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+        __syncwarp();
+        if (lane == 0) {
+            if (nmatch_out) nmatch_out[ti] = cnt;
+            const double mn = (double)min(la, lb);
+            const double bound = (double)((long long)R.k * cnt) / mn;
+            if (bound >= t_s) {
+                unsigned long long idx = atomicAdd(n_surv, 1ull);
+                if ((long long)idx < surv_cap)
+                    surv[idx] = (uint64_t)(uint32_t)ti | ((uint64_t)(cnt > 0xffffffffll ? 0xffffffffu : (uint32_t)cnt) << 32);
+                else
+                    atomicExch(ovf, 2);
+            }
+        }
+    }
+}
+
+// utils.cpp:26-55 in the reference's exact operation order, no FMA contraction.
+__device__ __forceinline__ double var_exact(const int32_t *d, int n) {
+    if (n == 0) return 0.0;
+    double sum = 0.0;
+    for (int i = 0; i < n; ++i) sum = __dadd_rn(sum, (double)d[i]);
+    const double dn = (double)n;
+    const double m = __ddiv_rn(sum, dn);
+    double ss = 0.0, comp = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double x = __dsub_rn((double)d[i], m);
+        ss = __dadd_rn(ss, __dmul_rn(x, x));
+        comp = __dadd_rn(comp, x);
+    }
+    // (ss - comp*comp/n) / (n-1): n-1 is computed in size_t, n==1 -> 0 -> x/0
+    return __ddiv_rn(__dsub_rn(ss, __ddiv_rn(__dmul_rn(comp, comp), dn)), (double)(n - 1));
+}
+
+struct Sink {
+    int mode;            // 0: none, 1: wave phase A (atomicMin acc[s*W+t] <- strand), 2: wave phase B (atomicMin best[t] <- 2s+strand)
+    uint32_t *acc;
+    int W;
+    uint32_t *best;
+    // test outputs, indexed by task (nullable)
+    int32_t *bases, *n_dist;
+    double *var;
+    uint8_t *accept;
+};
+
+// warp per survivor: emit matches, sort by (posA,posB), LIS on posB, chain filter, variance, accept test.
+// per-warp smem for cap C matches: keys u64[C] | prev i32[C] | tail i32[C+1] | tval i32[C+1]
+constexpr int PH_THREADS = 256;
+__host__ __device__ __forceinline__ size_t heavy_bytes(size_t n_pad, size_t n) {
+    return 8 * n_pad + 4 * n + 8 * (n + 1) + 16;
+}
+__global__ void __launch_bounds__(PH_THREADS) k_pair_heavy(TaskView tv, const uint64_t *__restrict__ tasks,
+                                                           const uint64_t *__restrict__ surv,
+                                                           const unsigned long long *n_surv_p, int64_t surv_cap,
+                                                           ReadView R, double t_s, double t_v, int cap_c,
+                                                           unsigned char *scratch, unsigned long long *scratch_cur,
+                                                           unsigned long long scratch_bytes, Sink S, int *ovf,
+                                                           unsigned long long *stat_heavy) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *wbase = sm_raw + (size_t)warp * heavy_bytes(cap_c, cap_c);
+    unsigned long long n_surv = *n_surv_p;
+    if ((long long)n_surv > surv_cap) n_surv = surv_cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && stat_heavy) atomicAdd(stat_heavy, n_surv);
+    const unsigned long long wstride = (unsigned long long)gridDim.x * (PH_THREADS / 32);
+    for (unsigned long long si = (unsigned long long)blockIdx.x * (PH_THREADS / 32) + warp; si < n_surv; si += wstride) {
+        const uint64_t rec = surv[si];
+        const uint32_t ti = (uint32_t)rec;
+        const uint32_t n32 = (uint32_t)(rec >> 32);
+        const uint64_t task = tasks[ti];
+        uint32_t ar, br;
+        int strand;
+        tv.decode(task, ar, br, strand);
+        const int la = R.len[ar], lb = R.len[br];
+        const int n1 = la - R.k, n2 = lb - R.k;
+        const uint32_t *A = R.kh[0] + R.koff(ar);
+        const uint32_t *B = (strand ? R.kh[1] : R.kh[0]) + R.koff(br);
+        const int32_t *PA = R.kp[0] + R.koff(ar);
+        const int32_t *PB = (strand ? R.kp[1] : R.kp[0]) + R.koff(br);
+        int bases = 0, nd = 0;
+        double v = 0.0;
+        bool fail = false;
+        if (n32 == 0xffffffffu) fail = true;
+        const int n = (int)n32;
+        int n_pad = 1;
+        while (n_pad < n) n_pad <<= 1;
+        uint64_t *keys = nullptr;
+        if (!fail) {
+            if (n_pad <= cap_c) {
+                keys = (uint64_t *)wbase;
+            } else {
+                unsigned long long need = (heavy_bytes(n_pad, n) + 15) & ~15ull, at = 0;
+                if (lane == 0) at = atomicAdd(scratch_cur, need);
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (at + need > scratch_bytes) fail = true;
+                else keys = (uint64_t *)(scratch + at);
+            }
+        }
+        if (fail) {
+            if (lane == 0) atomicExch(ovf, 3);
+            continue;
+        }
+        int32_t *prev = (int32_t *)(keys + n_pad);
+        int32_t *tail = prev + n;
+        int32_t *tval = tail + (n + 1);
+        if (n > 0) {
+            // emit
+            const int per = (n1 + 31) >> 5;
+            const int a0 = min(n1, lane * per), a1 = min(n1, a0 + per);
+            long long cnt = join_range<false>(A, B, a0, a1, n2, nullptr, nullptr, nullptr);
+            long long incl = cnt;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                long long o = __shfl_up_sync(0xffffffffu, incl, s);
+                if (lane >= s) incl += o;
+            }
+            join_range<true>(A, B, a0, a1, n2, PA, PB, keys + (incl - cnt));
+            for (int i = n + lane; i < n_pad; i += 32) keys[i] = ~0ull;
+            // warp bitonic sort
+            for (int size = 2; size <= n_pad; size <<= 1)
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    __syncwarp();
+                    for (int t = lane; t < (n_pad >> 1); t += 32) {
+                        int i = 2 * t - (t & (stride - 1));
+                        int j = i + stride;
+                        uint64_t a = keys[i], b = keys[j];
+                        bool asc = (i & size) == 0;
+                        if ((a > b) == asc) {
+                            keys[i] = b;
+                            keys[j] = a;
+                        }
+                    }
+                }
+            __syncwarp();
+            if (lane == 0) {
+                // similarity.cpp:10-31: patience LIS, strict on .second
+                int l = 0;
+                tail[0] = 0;
+                for (int i = 0; i < n; ++i) {
+                    const int vi = (int)(uint32_t)keys[i];
+                    int lo;
+                    if (l > 0 && tval[l] < vi) lo = l + 1;  // all tails smaller (tails strictly increase)
+                    else {
+                        lo = 1;
+                        int hi = l;
+                        while (lo <= hi) {
+                            int mid = (lo + hi + 1) >> 1;
+                            if (tval[mid] < vi) lo = mid + 1;
+                            else hi = mid - 1;
+                        }
+                    }
+                    prev[i] = tail[lo - 1];
+                    tail[lo] = i;
+                    tval[lo] = vi;
+                    if (lo > l) l = lo;
+                }
+                // similarity.cpp:36-44: backtrack; LIS indices overwrite tail[0..l)
+                int at = tail[l];
+                for (int i = l - 1; i >= 0; --i) {
+                    int nx = prev[at];
+                    tail[i] = at;
+                    at = nx;
+                }
+                // similarity.cpp:52-91: chain filter, covered bases, gap differences (into prev[])
+                const int k = R.k;
+                bases = k;
+                uint64_t lastk = keys[tail[0]];
+                int sprev = (int)(uint32_t)lastk;
+                for (int i = 1; i < l; ++i) {
+                    const uint64_t cur = keys[tail[i]];
+                    const int cf = (int)(cur >> 32), cs = (int)(uint32_t)cur;
+                    const int df = cf - (int)(lastk >> 32), ds = cs - (int)(uint32_t)lastk;
+                    if ((df < k && ds < k) || (df >= k && ds >= k)) {
+                        bases += k;
+                        const int ex = k - (cs - sprev);
+                        if (ex > 0) bases -= ex;
+                        prev[nd++] = ds - df;
+                        lastk = cur;
+                    }
+                    sprev = cs;
+                }
+                v = var_exact(prev, nd);
+            }
+        }
+        if (lane == 0) {
+            const double mn = (double)min(la, lb);
+            const bool ok = (__ddiv_rn((double)bases, mn) >= t_s) && (v < t_v);
+            if (S.bases) {
+                S.bases[ti] = bases;
+                S.n_dist[ti] = nd;
+                S.var[ti] = v;
+                S.accept[ti] = ok ? 1 : 0;
+            }
+            if (ok) {
+                const uint32_t t = (uint32_t)task;
+                const uint32_t s = (uint32_t)(task >> 33);
+                if (S.mode == 1) atomicMin(&S.acc[(size_t)s * S.W + t], (uint32_t)strand);
+                else if (S.mode == 2) atomicMin(&S.best[t], s * 2 + (uint32_t)strand);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ greedy wave bookkeeping
+// wave state (device): [0]=cursor, [1]=n_cand, [2]=n_seeds, [3]=done flag
+// k_select: one CTA scans items from the cursor and takes the first W untaken ones as this wave's candidates.
+__global__ void k_select(uint8_t *taken, int M, int W, int32_t *cand, int32_t *wave) {
+    __shared__ int s_count, s_base;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int cursor = wave[0];
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    int count = 0;
+    while (cursor < M && count < W) {
+        const int j = cursor + tid;
+        const bool un = j < M && !taken[j];
+        // block-level ordered compaction
+        const unsigned m = __ballot_sync(0xffffffffu, un);
+        __shared__ int wcnt[32];
+        const int lane = tid & 31, w = tid >> 5;
+        if (lane == 0) wcnt[w] = __popc(m);
+        __syncthreads();
+        if (tid == 0) {
+            int run = s_count;
+            s_base = run;
+            for (int i = 0; i < (nt >> 5); ++i) {
+                int c = wcnt[i];
+                wcnt[i] = run;
+                run += c;
+            }
+            s_count = run;
+        }
+        __syncthreads();
+        if (un) {
+            int slot = wcnt[w] + __popc(m & ((1u << lane) - 1u));
+            if (slot < W) cand[slot] = j;
+        }
+        __syncthreads();
+        count = s_count;
+        if (count >= W) {
+            // cursor must stop right after the W-th candidate: find it
+            break;
+        }
+        cursor += nt;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nc = min(s_count, W);
+        wave[1] = nc;
+        wave[2] = 0;
+        int newcur = nc ? cand[nc - 1] + 1 : M;
+        if (nc < W) newcur = M;  // scanned to the end
+        wave[0] = newcur;
+        wave[3] = (nc == 0) ? 1 : 0;
+    }
+}
+
+// mark candidates taken (after k_select so that the scan above reads a consistent state)
+__global__ void k_mark_cand(uint8_t *taken, const int32_t *cand, const int32_t *wave, int32_t *owner, uint8_t *owner_rev) {
+    const int nc = wave[1];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
+        taken[cand[i]] = 1;
+        owner[cand[i]] = cand[i];
+        owner_rev[cand[i]] = 0;
+    }
+}
+
+// k_resolve (one warp): greedy inside the wave (cluster.cpp:125-166 restricted to the candidates).
+// candidate b joins the smallest earlier candidate a that is a seed and matches it; otherwise it is a seed.
+__global__ void k_resolve(const uint32_t *acc, int W, const int32_t *cand, int32_t *wave, int32_t *seed_item,
+                          uint8_t *is_seed /*[W]*/, int32_t *owner, uint8_t *owner_rev) {
+    const int lane = threadIdx.x;
+    const int nc = wave[1];
+    int ns = 0;
+    for (int b = 0; b < nc; ++b) {
+        int found = -1;
+        for (int a0 = 0; a0 < b && found < 0; a0 += 32) {
+            const int a = a0 + lane;
+            bool hit = a < b && is_seed[a] && acc[(size_t)a * W + b] != 0xffffffffu;
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) found = a0 + __ffs(m) - 1;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (found >= 0) {
+                is_seed[b] = 0;
+                owner[cand[b]] = cand[found];
+                owner_rev[cand[b]] = (uint8_t)acc[(size_t)found * W + b];
+            } else {
+                is_seed[b] = 1;
+                seed_item[ns] = cand[b];
+            }
+        }
+        if (found < 0) ++ns;
+        __syncwarp();
+    }
+    if (lane == 0) wave[2] = ns;
+}
+
+// k_apply: targets that found a seed in phase B join it.
+__global__ void k_apply(uint32_t *best, int t0, int M, const int32_t *seed_item, uint8_t *taken, int32_t *owner,
+                        uint8_t *owner_rev) {
+    for (int j = t0 + blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
+        const uint32_t b = best[j];
+        if (b != 0xffffffffu) {
+            owner[j] = seed_item[b >> 1];
+            owner_rev[j] = (uint8_t)(b & 1u);
+            taken[j] = 1;
+            best[j] = 0xffffffffu;
+        }
+    }
+}
+
+__global__ void k_fill_u32(uint32_t *p, uint32_t v, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace rtl
