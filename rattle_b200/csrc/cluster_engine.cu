@@ -476,6 +476,7 @@ void cluster_run(rtl_ctx *ctx, int k, double t_s, double t_v, double bv_thr, dou
     const double t_begin = now_ms();
     const bool both = !is_rna;
     for (int c = 0; c < 4; ++c) S.ev.acc[c] = 0;
+    S.ex_k = -1;  // one call = the whole hot path: extraction is never reused across cluster_reads calls
     cluster_extract(ctx, k, both);
     const int N = (int)S.n;
     ensure_work_buffers(ctx, S, N);

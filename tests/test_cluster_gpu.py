@@ -209,3 +209,34 @@ def test_cluster_single_read_and_singletons(ctx, orc):
     one = synth.from_sequences(seqs[:1])
     got = ctx.cluster_reads(one.bases, one.offsets)
     assert got.n_clusters == 1 and list(got.mem_id) == [0]
+
+
+def _digest(cl):
+    import hashlib
+    h = hashlib.sha256()
+    for a in (cl.main_id, cl.main_rev, cl.cl_off, cl.mem_id, cl.mem_rev):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("genes", [400, 2000])
+def test_cluster_config2_full_size_matches_reference_digest(ctx, genes):
+    """BASELINE.json configs[1] at full size (2000 genes = 100 k reads): sha256 of the flat cluster set equals the
+    digest of the UNMODIFIED reference's output (tests/golden/config2_<genes>.json, made by
+    tests/golden/make_golden_config2.py from oracle/_ref; 92 s on 8 CPU threads at 100 k reads)."""
+    import hashlib
+    import json
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "config2_%d.json" % genes)
+    if not os.path.exists(path):
+        pytest.skip("golden not generated")
+    gold = json.load(open(path))
+    rs = synth.config2(n_genes=genes).sorted_by_length()[0]
+    assert hashlib.sha256(rs.bases.tobytes() + rs.offsets.tobytes()).hexdigest() == gold["input_sha256"]
+    cl = ctx.cluster_reads(rs.bases, rs.offsets, is_rna=False)
+    assert cl.n_clusters == gold["n_clusters"]
+    assert _digest(cl) == gold["sha256"]
+    # size-independent properties: a partition of the reads, every main_seq is a member of its cluster
+    assert sorted(cl.mem_id.tolist()) == list(range(rs.n))
+    for c in range(0, cl.n_clusters, 37):
+        assert cl.main_id[c] in cl.mem_id[cl.cl_off[c]:cl.cl_off[c + 1]]
