@@ -50,7 +50,8 @@ void rtl_destroy(rtl_ctx *ctx);
 const char *rtl_last_error(const rtl_ctx *ctx); /* ctx may be NULL: error of the last failed rtl_init */
 /* Tunables (all optional): "wave" = candidate seeds evaluated per greedy wave (default 512),
  * "task_cap" = candidate-pair buffer entries, "scratch_mb" = match scratch for oversized pairs,
- * "poa_batch" = alignments in flight. Returns RTL_ERR_INPUT for an unknown key. */
+ * "poa_arena_mb" = device memory for POA score rows + traceback codes (set before the first POA call).
+ * Returns RTL_ERR_INPUT for an unknown key. */
 int rtl_set_option(rtl_ctx *ctx, const char *key, int64_t value);
 
 /* Run all work of this ctx on an existing CUDA stream (a cudaStream_t passed as void*; NULL = the ctx's own

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librattle_b200.so")
-SOURCES = ["capi.cu", "cluster_engine.cu", "poa_engine.cu", "hps_codec.cpp"]
+SOURCES = ["capi.cu", "cluster_engine.cu", "poa_engine.cu", "correct_engine.cu", "hps_codec.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-Wall", "--fmad=false"]
 

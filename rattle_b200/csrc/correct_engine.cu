@@ -1,0 +1,436 @@
+// correct_reads (correct.cpp:311-563) on top of the batched GPU POA driver.  The POA (91 % of the reference's time)
+// runs on the device for all packs at once; the MSA post-processing (fix_msa_ends, column vote, read correction —
+// <2 % of the reference's time, double arithmetic whose summation order and libm calls must match) runs on host
+// threads, one pack per thread, and follows the reference's single-threaded pack order.
+#include <math.h>
+
+#include <algorithm>
+#include <cstring>
+#include <sstream>
+
+#include "common.cuh"
+#include "poa_engine.hpp"
+
+namespace {
+
+struct Read {
+    std::string header, seq, ann, quality;
+};
+
+// utils.cpp:6-13
+inline char phred_symbol(double p) { return (char)(-10 * log10(p) + 33); }
+inline double phred_err(char c) {
+    double q = c - 33;
+    return pow(10.0, -q / 10.0);
+}
+
+// utils.cpp:15-24 with utils.hpp:7-13
+std::string reverse_complement(const std::string &s) {
+    std::string r = s;
+    const int len = (int)s.size();
+    for (int i = 0; i < len; ++i) {
+        char c = s[len - 1 - i], o;
+        switch (c) {
+            case 'A': o = 'T'; break;
+            case 'C': o = 'G'; break;
+            case 'T': o = 'A'; break;
+            case 'G': o = 'C'; break;
+            case 'U': o = 'A'; break;
+            default: throw InputError("base outside ACGTU in a reverse-strand cluster member (utils.cpp:20)");
+        }
+        r[i] = o;
+    }
+    return r;
+}
+
+// correct.cpp:32-92, literally (including the case where a fully blanked row is left reversed)
+void fix_msa_ends(std::vector<Read> &reads, std::vector<std::string> &aln) {
+    for (size_t i = 0; i < aln.size(); ++i) {
+        bool reversed = false;
+        std::string &row = aln[i];
+    remove_blocks:
+        int pos = 0, end_pos = 0;
+        const int n = (int)row.size();
+        while (pos < n) {
+            while (pos < n && row[pos] == '-') ++pos;
+            end_pos = pos;
+            int gaps = 0, sz = 0;
+            while (gaps < 4 && end_pos < n) {
+                if (row[end_pos] == '-') ++gaps;
+                else {
+                    ++sz;
+                    gaps = 0;
+                }
+                ++end_pos;
+            }
+            bool flip = true;
+            if (sz < 10) {
+                while (end_pos < n && row[end_pos] == '-') {
+                    ++end_pos;
+                    ++gaps;
+                }
+                if (gaps >= 20) {
+                    for (int j = pos; j < end_pos; ++j) row[j] = '-';
+                    reads[i].quality.erase(0, sz);
+                    reads[i].seq.erase(0, sz);
+                    pos = end_pos;
+                    flip = false;
+                }
+            }
+            if (flip) {
+                std::reverse(row.begin(), row.end());
+                std::reverse(reads[i].quality.begin(), reads[i].quality.end());
+                std::reverse(reads[i].seq.begin(), reads[i].seq.end());
+                if (!reversed) {
+                    reversed = true;
+                    goto remove_blocks;
+                }
+                break;
+            }
+        }
+    }
+}
+
+// Column statistics of generate_consensus_vector (correct.cpp:94-193).  Symbols are indexed in the iteration order
+// of the reference's std::unordered_map<char,pos_info_t> (insertion A,C,T,U,G,'-' -> iteration U,'-',G,T,C,A with
+// libstdc++), because the strict '>' vote keeps the first symbol in that order on ties.
+constexpr int NSYM = 6;
+const char SYM[NSYM] = {'U', '-', 'G', 'T', 'C', 'A'};
+inline int sym_index(char c) {
+    switch (c) {
+        case 'U': return 0;
+        case '-': return 1;
+        case 'G': return 2;
+        case 'T': return 3;
+        case 'C': return 4;
+        case 'A': return 5;
+        default: return -1;
+    }
+}
+struct ColStats {
+    std::vector<int> occ, total_occ;  // [col*6 + sym]
+    std::vector<double> err;
+    std::vector<char> consensus;
+};
+
+void consensus_vector(const std::vector<Read> &reads, const std::vector<std::string> &aln, ColStats &cs) {
+    cs.occ.clear();
+    cs.total_occ.clear();
+    cs.err.clear();
+    cs.consensus.clear();
+    if (reads.empty() || aln.empty()) return;
+    const size_t ncol = aln[0].size();
+    cs.occ.assign(ncol * NSYM, 0);
+    cs.total_occ.assign(ncol * NSYM, 0);
+    cs.err.assign(ncol * NSYM, 0.0);
+    for (size_t i = 0; i < reads.size(); ++i) {
+        const std::string &row = aln[i];
+        const std::string &qual = reads[i].quality;
+        int seq_pos = -1;
+        for (size_t k = 0; k < row.size(); ++k) {
+            const char nt = row[k];
+            double err_p = 0.0;
+            if (nt != '-') {
+                ++seq_pos;
+                err_p = phred_err(qual[seq_pos]);
+            }
+            if (seq_pos >= 0 && (size_t)seq_pos < qual.size()) {
+                const int s = sym_index(nt);
+                if (s < 0) throw InputError("base outside ACGTU in a read to correct");
+                cs.occ[k * NSYM + s]++;
+                cs.err[k * NSYM + s] += err_p;
+                if ((size_t)seq_pos == qual.size() - 1) ++seq_pos;  // end of read: trailing gaps do not vote
+            }
+        }
+    }
+    cs.consensus.resize(ncol);
+    for (size_t k = 0; k < ncol; ++k) {
+        int max_occ = 0;
+        char max_nt = 0;
+        int tot = 0;
+        for (int s = 0; s < NSYM; ++s) tot += cs.occ[k * NSYM + s];
+        for (int s = 0; s < NSYM; ++s) {
+            const int o = cs.occ[k * NSYM + s];
+            if (o > 0) {
+                cs.total_occ[k * NSYM + s] += tot;
+                cs.err[k * NSYM + s] /= double(o);
+            }
+            if (o > max_occ) {
+                max_occ = o;
+                max_nt = SYM[s];
+            }
+        }
+        if (max_nt == 0) max_nt = '-';
+        cs.consensus[k] = max_nt;
+    }
+}
+
+std::string strip_gaps(const std::vector<char> &c) {
+    std::string s;
+    s.reserve(c.size());
+    for (char x : c)
+        if (x != '-') s.push_back(x);
+    return s;
+}
+
+// correct.cpp:196-309 (err_ratio is the literal 30.0 the reference passes at correct.cpp:409)
+void correct_pack(const std::vector<Read> &reads, const std::vector<std::string> &aln, double min_occ, double gap_occ,
+                  double err_ratio, std::vector<Read> &corrected, std::vector<Read> &uncorrected) {
+    ColStats cs;
+    consensus_vector(reads, aln, cs);
+    for (size_t i = 0; i < reads.size(); ++i) {
+        const std::string &row = aln[i];
+        const std::string &qual = reads[i].quality;
+        int seq_pos = -1;
+        std::string res_read, res_qt;
+        for (size_t k = 0; k < row.size(); ++k) {
+            const char nt = row[k];
+            double err_p = 0.0;
+            if (nt != '-') {
+                ++seq_pos;
+                err_p = phred_err(qual[seq_pos]);
+            }
+            if (seq_pos >= 0 && (size_t)seq_pos < qual.size()) {
+                const char cnt = cs.consensus[k];
+                const int ci = sym_index(cnt);
+                const double c_err = cs.err[k * NSYM + ci];
+                const double occ_ratio = double(cs.occ[k * NSYM + ci]) / double(cs.total_occ[k * NSYM + ci]);
+                if (cnt == '-') {
+                    if (nt != '-') {
+                        if (!(occ_ratio >= gap_occ)) {
+                            res_read += nt;
+                            res_qt += qual[seq_pos];
+                        }
+                    }
+                } else {
+                    if (nt == '-') {
+                        if (occ_ratio >= gap_occ) {
+                            res_read += cnt;
+                            res_qt += phred_symbol(c_err);
+                        }
+                    } else if (nt == cnt) {
+                        res_read += nt;
+                        res_qt += qual[seq_pos];
+                    } else if (occ_ratio >= min_occ && err_ratio * err_p > c_err) {
+                        res_read += cnt;
+                        res_qt += phred_symbol(c_err);
+                    } else {
+                        res_read += nt;
+                        res_qt += qual[seq_pos];
+                    }
+                }
+                if ((size_t)seq_pos == qual.size() - 1) ++seq_pos;
+            }
+        }
+        if (!res_read.empty()) corrected.push_back(Read{reads[i].header, res_read, "+", res_qt});
+        else uncorrected.push_back(reads[i]);
+    }
+}
+
+std::vector<std::string> split_string(const std::string &str, char delim) {  // correct.cpp:20-30
+    std::vector<std::string> out;
+    std::stringstream ss(str);
+    std::string tok;
+    while (getline(ss, tok, delim)) out.push_back(tok);
+    return out;
+}
+
+void append_fastq(std::string &dst, const std::vector<Read> &rs) {  // fasta.cpp:436-445
+    for (const auto &r : rs) {
+        dst += r.header;
+        dst += '\n';
+        dst += r.seq;
+        dst += '\n';
+        dst += r.ann;
+        dst += '\n';
+        dst += r.quality;
+        dst += '\n';
+    }
+}
+
+struct Pack {
+    int cid;
+    std::vector<Read> creads;
+    std::vector<Read> corrected, uncorrected, sorted_corrected;
+    PoaTask t1, t2;
+    std::string consensus;
+};
+
+void set_task(PoaTask &t, const std::vector<Read> &rs) {
+    t.seq.clear();
+    t.len.clear();
+    for (const auto &r : rs) {
+        t.seq.push_back(r.seq.data());
+        t.len.push_back((int)r.seq.size());
+    }
+}
+
+}  // namespace
+
+int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const uint64_t *offsets, uint32_t n_reads,
+                       const char *headers, const uint64_t *header_off, const int32_t *main_id, const uint8_t *main_rev,
+                       const int32_t *main_gene, const int64_t *cl_off, const int32_t *mem_id, const uint8_t *mem_rev,
+                       const int32_t *mem_gene, int n_clusters, double min_occ, double gap_occ, double err_ratio,
+                       int split, int min_reads, char *corrected_out, int64_t *corrected_len, char *uncorrected_out,
+                       int64_t *uncorrected_len, char *consensi_out, int64_t *consensi_len) {
+    (void)main_id;
+    (void)main_rev;
+    (void)mem_gene;
+    (void)err_ratio;  // the reference ignores it too: correct.cpp:409 passes the literal 30.0
+    const double t0 = now_ms();
+    ctx->stats = rtl_stats{};
+    if (n_clusters < 1) throw InputError("empty cluster set (correct.cpp:322 reads clusters[0])");
+    if (split < 1) throw InputError("split must be >= 1");
+    const int nthreads = host_threads();
+    std::vector<Read> reads(n_reads);
+    for (uint32_t i = 0; i < n_reads; ++i) {
+        if (headers) reads[i].header.assign(headers + header_off[i], headers + header_off[i + 1]);
+        else reads[i].header = "@r" + std::to_string(i);
+        reads[i].seq.assign(bases + offsets[i], bases + offsets[i + 1]);
+        reads[i].ann = "+";
+        reads[i].quality.assign(quals + offsets[i], quals + offsets[i + 1]);
+    }
+    const bool gene_mode = (main_gene ? main_gene[0] : -1) == -1;
+
+    // ---- pack construction (correct.cpp:328-370)
+    std::vector<Read> uncorrected_set, corrected_set, consensus_set;
+    std::vector<Pack> packs;
+    for (int cid = 0; cid < n_clusters; ++cid) {
+        const int64_t b = cl_off[cid];
+        const size_t n = (size_t)(cl_off[cid + 1] - b);
+        if (n == 0) throw InputError("cluster without members");
+        const int n_files = (int)((n - 1) / split + 1);
+        const int gid = main_gene ? main_gene[cid] : -1;
+        for (int nf = 0; nf < n_files; ++nf) {
+            std::vector<Read> creads;
+            for (size_t j = nf; j < n; j += n_files) {
+                const int id = mem_id[b + j];
+                if (id < 0 || (uint32_t)id >= n_reads) throw InputError("cluster member index out of range");
+                Read &r = reads[id];
+                if (mem_rev[b + j]) {
+                    r.seq = reverse_complement(r.seq);
+                    std::reverse(r.quality.begin(), r.quality.end());
+                }
+                if (gid == -1) r.header = r.header + ",gene_cluster_" + std::to_string(cid);
+                else r.header = r.header + ",gene_cluster_" + std::to_string(gid) + ",transcript_cluster_" + std::to_string(cid);
+                creads.push_back(r);
+            }
+            if ((int)creads.size() > min_reads) {
+                packs.emplace_back();
+                packs.back().cid = cid;
+                packs.back().creads = std::move(creads);
+            } else {
+                for (auto &r : creads) uncorrected_set.push_back(r);
+            }
+        }
+    }
+
+    // ---- POA round 1 on the raw reads of every pack (correct.cpp:395-405)
+    std::vector<PoaTask *> tasks;
+    for (auto &p : packs) {
+        set_task(p.t1, p.creads);
+        tasks.push_back(&p.t1);
+    }
+    poa_run(ctx, tasks, 5, -4, -8, -6, false);
+    parallel_for(nthreads, packs.size(), [&](size_t i) {
+        Pack &p = packs[i];
+        std::vector<std::string> msa;
+        p.t1.g.msa(msa);
+        p.t1.g.clear();
+        fix_msa_ends(p.creads, msa);
+        correct_pack(p.creads, msa, min_occ, gap_occ, 30.0, p.corrected, p.uncorrected);
+        p.sorted_corrected = p.corrected;
+        std::stable_sort(p.sorted_corrected.begin(), p.sorted_corrected.end(),
+                         [](const Read &a, const Read &b) { return a.seq.size() > b.seq.size(); });  // fasta.cpp:458-464
+    });
+    for (auto &p : packs) {  // queue order = the reference's -t 1 order (correct.cpp:413-424)
+        for (auto &r : p.corrected) corrected_set.push_back(r);
+        for (auto &r : p.uncorrected) uncorrected_set.push_back(r);
+    }
+
+    // ---- POA round 2 on the corrected reads (correct.cpp:427-445)
+    tasks.clear();
+    for (auto &p : packs) {
+        set_task(p.t2, p.sorted_corrected);
+        tasks.push_back(&p.t2);
+    }
+    poa_run(ctx, tasks, 5, -4, -8, -6, false);
+    parallel_for(nthreads, packs.size(), [&](size_t i) {
+        Pack &p = packs[i];
+        std::vector<std::string> msa;
+        p.t2.g.msa(msa);
+        p.t2.g.clear();
+        fix_msa_ends(p.sorted_corrected, msa);
+        ColStats cs;
+        consensus_vector(p.sorted_corrected, msa, cs);
+        p.consensus = strip_gaps(cs.consensus);
+    });
+
+    // ---- pack consensus headers (correct.cpp:447-470; no file labels through this entry point)
+    std::vector<std::vector<Read>> consensi(n_clusters);
+    for (auto &p : packs) {
+        std::string gid;
+        for (const auto &r : p.creads) {
+            const size_t index = r.header.find("gene_cluster");
+            gid = std::to_string(std::stoi(r.header.substr(index + 13)));
+        }
+        consensi[p.cid].push_back(Read{gid + "," + std::to_string(p.creads.size()) + ",", p.consensus, "+",
+                                       std::string(p.consensus.size(), 'K')});
+    }
+
+    // ---- clusters with several packs: third POA over the pack consensi (correct.cpp:518-538)
+    std::vector<PoaTask> t3(n_clusters);
+    tasks.clear();
+    for (int cid = 0; cid < n_clusters; ++cid)
+        if (consensi[cid].size() > 1) {
+            set_task(t3[cid], consensi[cid]);
+            tasks.push_back(&t3[cid]);
+        }
+    if (!tasks.empty()) poa_run(ctx, tasks, 5, -4, -8, -6, false);
+    for (int cid = 0; cid < n_clusters; ++cid) {
+        auto &it = consensi[cid];
+        int total_reads = 0, gid = 0;
+        for (const auto &r : it) {
+            auto num = split_string(r.header, ',');
+            gid = std::stoi(num[0]);
+            total_reads += std::stoi(num[1]);
+        }
+        const std::string head = gene_mode
+                                     ? "@gene_cluster_" + std::to_string(cid) + " reads=" + std::to_string(total_reads) + " labels="
+                                     : "@transcript_cluster_" + std::to_string(cid) + " gene_cluster_" + std::to_string(gid) +
+                                           " reads=" + std::to_string(total_reads) + " labels=";
+        if (it.size() > 1) {
+            std::vector<std::string> msa;
+            t3[cid].g.msa(msa);
+            fix_msa_ends(it, msa);
+            ColStats cs;
+            consensus_vector(it, msa, cs);
+            const std::string consensus = strip_gaps(cs.consensus);
+            consensus_set.push_back(Read{head, consensus, "+", std::string(consensus.size(), 'K')});
+        } else if (it.size() == 1) {
+            consensus_set.push_back(Read{head, it[0].seq, "+", it[0].quality});
+        }
+    }
+
+    std::string out_c, out_u, out_s;
+    append_fastq(out_c, corrected_set);
+    append_fastq(out_u, uncorrected_set);
+    append_fastq(out_s, consensus_set);
+    int rc = RTL_OK;
+    auto put = [&](const std::string &s, char *buf, int64_t *len) {
+        if ((int64_t)s.size() > *len || !buf) {
+            *len = (int64_t)s.size();
+            rc = RTL_ERR_CAPACITY;
+            return;
+        }
+        memcpy(buf, s.data(), s.size());
+        *len = (int64_t)s.size();
+    };
+    put(out_c, corrected_out, corrected_len);
+    put(out_u, uncorrected_out, uncorrected_len);
+    put(out_s, consensi_out, consensi_len);
+    ctx->stats.total_ms = now_ms() - t0;
+    ctx->stats.d2h_bytes += (int64_t)(out_c.size() + out_u.size() + out_s.size());
+    if (rc == RTL_ERR_CAPACITY) ctx->err = "output buffer too small (needed sizes returned in *_len)";
+    return rc;
+}
