@@ -97,17 +97,6 @@ def make_workload(genes):
     return rs.sorted_by_length()[0]  # main.cpp:254 sort_read_set
 
 
-def have_correct(ctx):
-    try:
-        tiny = synth.generate(seed=1, n_genes=1, reads_per_tx=2, len_mean=100.0, len_sd=0.0, len_min=100, len_max=100)
-        ctx.poa_msa(tiny.bases, tiny.offsets)
-        return True
-    except Exception as e:
-        if "not built" in str(e):
-            return False
-        raise
-
-
 def reference_arm(args, rank, world):
     """Unmodified reference on the host cores (rank 0 only)."""
     if rank != 0:
@@ -170,7 +159,7 @@ def main():
 
     if args.impl == "reference":
         if args.correct is None:
-            args.correct = os.path.exists(os.path.join(ROOT, "rattle_b200", "csrc", "poa_kernels.cuh"))
+            args.correct = True
         reference_arm(args, rank, world)
         return
 
@@ -185,21 +174,11 @@ def main():
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     if args.correct is None:
-        args.correct = have_correct(ctx)
+        args.correct = True
 
     if world > 1:
-        class _Dev:  # zero-copy view of a raw device pointer for torch.distributed
-            def __init__(self, ptr, n):
-                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3}
-
-        def allreduce_min(ptr, count):
-            # unsigned min through NCCL's int32 MIN: x ^ 0x80000000 maps uint32 order onto int32 order (in place)
-            t = torch.as_tensor(_Dev(ptr, count), device="cuda")
-            t.bitwise_xor_(-2147483648)
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            t.bitwise_xor_(-2147483648)
-            return 0
-        ctx.set_shard(rank, world, allreduce_min)
+        from rattle_b200.dist import make_allreduce_callback
+        ctx.set_shard(rank, world, make_allreduce_callback())
 
     rs = make_workload(args.genes)
     n_reads = rs.n
@@ -220,14 +199,8 @@ def main():
         if world == 1:
             sub = cl
         else:
-            keep = np.arange(cl.n_clusters) % world == rank
-            sizes = np.diff(cl.cl_off)
-            off = np.zeros(int(keep.sum()) + 1, np.int64)
-            off[1:] = np.cumsum(sizes[keep])
-            mask = np.repeat(keep, sizes)
-            sub = rattle_b200.ClusterSet(cl.main_id[keep].copy(), cl.main_rev[keep].copy(), off,
-                                         cl.mem_id[:int(cl.cl_off[-1])][mask].copy(),
-                                         cl.mem_rev[:int(cl.cl_off[-1])][mask].copy())
+            from rattle_b200.dist import shard_clusters
+            sub, _ = shard_clusters(cl, rank, world)
         return ctx.correct_reads(bases_np, quals_np, rs.offsets, sub, **CORRECT_KW)
 
     def step_resident():

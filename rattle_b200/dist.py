@@ -1,0 +1,53 @@
+"""Multi-GPU host logic (one process per GPU, torch.distributed for the plumbing).
+
+clustering: every rank holds the whole read set (extraction is replicated), evaluates the (seed,target) pairs of each
+            greedy wave whose target index t has t % world == rank, and the per-wave decision arrays (uint32, smaller
+            wins, 0xffffffff = none) are min-reduced across ranks — the one real exchange step of the path.
+correction: independent clusters -> round-robin shards, no collective.
+"""
+import numpy as np
+
+
+def allreduce_min_u32_(t, group=None):
+    """In-place unsigned-min all-reduce of an int32 tensor that holds uint32 bit patterns.
+    x ^ 0x80000000 maps uint32 order onto int32 order, so the backend's signed MIN does the unsigned reduction."""
+    import torch.distributed as dist
+    t.bitwise_xor_(-2147483648)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    t.bitwise_xor_(-2147483648)
+    return t
+
+
+class _DevView:
+    """zero-copy view of a raw device pointer (the decision arrays live in librattle_b200's own allocations)"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+
+
+def make_allreduce_callback(group=None):
+    """callback(ptr, count) for Context.set_shard: min-reduces `count` uint32 at device pointer `ptr` over NCCL"""
+    import torch
+
+    def cb(ptr, count):
+        t = torch.as_tensor(_DevView(ptr, count), device="cuda")
+        allreduce_min_u32_(t, group)
+        return 0
+    return cb
+
+
+def shard_clusters(cl, rank, world):
+    """clusters rank, rank+world, ... of a ClusterSet, with their global cluster ids"""
+    from .api import ClusterSet
+    nc = cl.n_clusters
+    keep = (np.arange(nc) % world) == rank
+    sizes = np.diff(cl.cl_off)
+    off = np.zeros(int(keep.sum()) + 1, np.int64)
+    off[1:] = np.cumsum(sizes[keep])
+    mask = np.repeat(keep, sizes)
+    total = int(cl.cl_off[-1])
+    sub = ClusterSet(cl.main_id[keep].copy(), cl.main_rev[keep].copy(), off, cl.mem_id[:total][mask].copy(),
+                     cl.mem_rev[:total][mask].copy(),
+                     None if cl.main_gene is None else cl.main_gene[keep].copy(),
+                     None if cl.mem_gene is None else cl.mem_gene[:total][mask].copy())
+    return sub, np.nonzero(keep)[0]
