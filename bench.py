@@ -273,7 +273,8 @@ def main():
     bv_gbs = bv_alg_bytes / (st["bv_ms"] * 1e-3) / 1e9 if st["bv_ms"] > 0 else 0.0
     if dom == "poa":
         cells = st2["poa_cells"]
-        gb = cells * 2 / (st2["poa_ms"] * 1e-3) / 1e9  # 2 B of traceback code written per DP cell
+        # algorithmic bytes per DP cell: 2 B traceback code + 4 B (H,F) row cell written once
+        gb = cells * 6 / (st2["poa_ms"] * 1e-3) / 1e9
         roof = {"kernel": "k_poa_align", "bound": "hbm", "achieved": gb, "peak": hbm, "unit": "GB/s", "frac": gb / hbm,
                 "traffic": None, "peak_source": peak_src, "gcups": cells / (st2["poa_ms"] * 1e-3) / 1e9,
                 "launches": st2["poa_launches"], "avg_launch_ms": st2["poa_ms"] / max(1, st2["poa_launches"])}

@@ -55,6 +55,16 @@ struct DevBuf {
         }
         return p;
     }
+    // for buffers that grow step by step inside a pipeline: cudaFree synchronises the device, so grow geometrically
+    T *need_geo(size_t n) {
+        if (n > cap) {
+            release();
+            size_t want = 2 * n + 64;
+            CK(cudaMalloc((void **)&p, want * sizeof(T)));
+            cap = want;
+        }
+        return p;
+    }
 };
 
 // pinned host staging buffer (grow-only)
@@ -71,6 +81,15 @@ struct PinBuf {
             p = nullptr;
             CK(cudaMallocHost((void **)&p, (n + 64) * sizeof(T)));
             cap = n + 64;
+        }
+        return p;
+    }
+    T *need_geo(size_t n) {
+        if (n > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            CK(cudaMallocHost((void **)&p, (2 * n + 64) * sizeof(T)));
+            cap = 2 * n + 64;
         }
         return p;
     }

@@ -5,6 +5,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 
@@ -19,9 +20,20 @@ struct Read {
 
 // utils.cpp:6-13
 inline char phred_symbol(double p) { return (char)(-10 * log10(p) + 33); }
-inline double phred_err(char c) {
+inline double phred_err_exact(char c) {
     double q = c - 33;
     return pow(10.0, -q / 10.0);
+}
+// same libm pow() values, tabulated once per byte value (the column vote calls this for every base twice)
+struct PhredTable {
+    double v[256];
+    PhredTable() {
+        for (int i = 0; i < 256; ++i) v[i] = phred_err_exact((char)i);
+    }
+};
+inline double phred_err(char c) {
+    static const PhredTable T;
+    return T.v[(unsigned char)c];
 }
 
 // utils.cpp:15-24 with utils.hpp:7-13
@@ -250,10 +262,15 @@ void append_fastq(std::string &dst, const std::vector<Read> &rs) {  // fasta.cpp
 
 struct Pack {
     int cid;
+    int64_t first;  // offset of the cluster in the member arrays
+    int nf, n_files;
+    size_t n;       // cluster size
+    bool small = false;
     std::vector<Read> creads;
     std::vector<Read> corrected, uncorrected, sorted_corrected;
     PoaTask t1, t2;
     std::string consensus;
+    std::string fq_corrected, fq_uncorrected;  // FASTQ text of this pack's outputs
 };
 
 void set_task(PoaTask &t, const std::vector<Read> &rs) {
@@ -278,53 +295,108 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
     (void)mem_gene;
     (void)err_ratio;  // the reference ignores it too: correct.cpp:409 passes the literal 30.0
     const double t0 = now_ms();
+    const bool trace = getenv("RTL_TRACE") != nullptr;
+    double t_last = t0;
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        const double t = now_ms();
+        fprintf(stderr, "[rtl] correct %-28s %9.1f ms\n", what, t - t_last);
+        t_last = t;
+    };
     ctx->stats = rtl_stats{};
     if (n_clusters < 1) throw InputError("empty cluster set (correct.cpp:322 reads clusters[0])");
     if (split < 1) throw InputError("split must be >= 1");
     const int nthreads = host_threads();
-    std::vector<Read> reads(n_reads);
-    for (uint32_t i = 0; i < n_reads; ++i) {
-        if (headers) reads[i].header.assign(headers + header_off[i], headers + header_off[i + 1]);
-        else reads[i].header = "@r" + std::to_string(i);
-        reads[i].seq.assign(bases + offsets[i], bases + offsets[i + 1]);
-        reads[i].ann = "+";
-        reads[i].quality.assign(quals + offsets[i], quals + offsets[i + 1]);
-    }
     const bool gene_mode = (main_gene ? main_gene[0] : -1) == -1;
 
-    // ---- pack construction (correct.cpp:328-370)
-    std::vector<Read> uncorrected_set, corrected_set, consensus_set;
+    // ---- pack construction (correct.cpp:328-370).  Every read belongs to one pack, so packs are built in parallel
+    // straight from the flat input; a read listed twice would be reverse-complemented / re-labelled twice by the
+    // reference (it edits the shared read in place), which the serial fallback below reproduces.
     std::vector<Pack> packs;
     for (int cid = 0; cid < n_clusters; ++cid) {
-        const int64_t b = cl_off[cid];
-        const size_t n = (size_t)(cl_off[cid + 1] - b);
+        const size_t n = (size_t)(cl_off[cid + 1] - cl_off[cid]);
         if (n == 0) throw InputError("cluster without members");
         const int n_files = (int)((n - 1) / split + 1);
-        const int gid = main_gene ? main_gene[cid] : -1;
         for (int nf = 0; nf < n_files; ++nf) {
-            std::vector<Read> creads;
-            for (size_t j = nf; j < n; j += n_files) {
-                const int id = mem_id[b + j];
-                if (id < 0 || (uint32_t)id >= n_reads) throw InputError("cluster member index out of range");
-                Read &r = reads[id];
-                if (mem_rev[b + j]) {
+            packs.emplace_back();
+            Pack &p = packs.back();
+            p.cid = cid;
+            p.first = cl_off[cid];
+            p.nf = nf;
+            p.n_files = n_files;
+            p.n = n;
+        }
+    }
+    bool duplicates = false;
+    {
+        std::vector<uint8_t> seen(n_reads, 0);
+        const int64_t total = cl_off[n_clusters];
+        for (int64_t i = 0; i < total; ++i) {
+            const int id = mem_id[i];
+            if (id < 0 || (uint32_t)id >= n_reads) throw InputError("cluster member index out of range");
+            if (seen[id]) duplicates = true;
+            seen[id] = 1;
+        }
+    }
+    auto suffix = [&](int cid) {
+        const int gid = main_gene ? main_gene[cid] : -1;
+        return gid == -1 ? ",gene_cluster_" + std::to_string(cid)
+                         : ",gene_cluster_" + std::to_string(gid) + ",transcript_cluster_" + std::to_string(cid);
+    };
+    if (!duplicates) {
+        parallel_for(nthreads, packs.size(), [&](size_t pi) {
+            Pack &p = packs[pi];
+            const std::string suf = suffix(p.cid);
+            for (size_t j = p.nf; j < p.n; j += p.n_files) {
+                const int id = mem_id[p.first + j];
+                Read r;
+                if (headers) r.header.assign(headers + header_off[id], headers + header_off[id + 1]);
+                else r.header = "@r" + std::to_string(id);
+                r.header += suf;
+                r.seq.assign(bases + offsets[id], bases + offsets[id + 1]);
+                r.ann = "+";
+                r.quality.assign(quals + offsets[id], quals + offsets[id + 1]);
+                if (mem_rev[p.first + j]) {
                     r.seq = reverse_complement(r.seq);
                     std::reverse(r.quality.begin(), r.quality.end());
                 }
-                if (gid == -1) r.header = r.header + ",gene_cluster_" + std::to_string(cid);
-                else r.header = r.header + ",gene_cluster_" + std::to_string(gid) + ",transcript_cluster_" + std::to_string(cid);
-                creads.push_back(r);
+                p.creads.push_back(std::move(r));
             }
-            if ((int)creads.size() > min_reads) {
-                packs.emplace_back();
-                packs.back().cid = cid;
-                packs.back().creads = std::move(creads);
-            } else {
-                for (auto &r : creads) uncorrected_set.push_back(r);
+        });
+    } else {
+        std::vector<Read> reads(n_reads);
+        for (uint32_t i = 0; i < n_reads; ++i) {
+            if (headers) reads[i].header.assign(headers + header_off[i], headers + header_off[i + 1]);
+            else reads[i].header = "@r" + std::to_string(i);
+            reads[i].seq.assign(bases + offsets[i], bases + offsets[i + 1]);
+            reads[i].ann = "+";
+            reads[i].quality.assign(quals + offsets[i], quals + offsets[i + 1]);
+        }
+        for (auto &p : packs) {
+            const std::string suf = suffix(p.cid);
+            for (size_t j = p.nf; j < p.n; j += p.n_files) {
+                Read &r = reads[mem_id[p.first + j]];
+                if (mem_rev[p.first + j]) {
+                    r.seq = reverse_complement(r.seq);
+                    std::reverse(r.quality.begin(), r.quality.end());
+                }
+                r.header = r.header + suf;
+                p.creads.push_back(r);
             }
         }
     }
-
+    // packs that are too small are not corrected (correct.cpp:360-366); their reads go to `uncorrected` first
+    std::string out_c, out_u, out_s;
+    {
+        std::vector<Pack> keep;
+        keep.reserve(packs.size());
+        for (auto &p : packs) {
+            if ((int)p.creads.size() > min_reads) keep.push_back(std::move(p));
+            else append_fastq(out_u, p.creads);
+        }
+        packs.swap(keep);
+    }
+    lap("pack construction");
     // ---- POA round 1 on the raw reads of every pack (correct.cpp:395-405)
     std::vector<PoaTask *> tasks;
     for (auto &p : packs) {
@@ -332,6 +404,7 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
         tasks.push_back(&p.t1);
     }
     poa_run(ctx, tasks, 5, -4, -8, -6, false);
+    lap("POA round 1");
     parallel_for(nthreads, packs.size(), [&](size_t i) {
         Pack &p = packs[i];
         std::vector<std::string> msa;
@@ -339,15 +412,31 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
         p.t1.g.clear();
         fix_msa_ends(p.creads, msa);
         correct_pack(p.creads, msa, min_occ, gap_occ, 30.0, p.corrected, p.uncorrected);
+        append_fastq(p.fq_corrected, p.corrected);
+        append_fastq(p.fq_uncorrected, p.uncorrected);
         p.sorted_corrected = p.corrected;
         std::stable_sort(p.sorted_corrected.begin(), p.sorted_corrected.end(),
                          [](const Read &a, const Read &b) { return a.seq.size() > b.seq.size(); });  // fasta.cpp:458-464
     });
-    for (auto &p : packs) {  // queue order = the reference's -t 1 order (correct.cpp:413-424)
-        for (auto &r : p.corrected) corrected_set.push_back(r);
-        for (auto &r : p.uncorrected) uncorrected_set.push_back(r);
+    // queue order = the reference's -t 1 order (correct.cpp:413-424)
+    {
+        size_t nc = 0, nu = out_u.size();
+        for (auto &p : packs) {
+            nc += p.fq_corrected.size();
+            nu += p.fq_uncorrected.size();
+        }
+        out_c.reserve(nc);
+        out_u.reserve(nu);
+        for (auto &p : packs) {
+            out_c += p.fq_corrected;
+            out_u += p.fq_uncorrected;
+            std::string().swap(p.fq_corrected);
+            std::string().swap(p.fq_uncorrected);
+            std::vector<Read>().swap(p.corrected);
+            std::vector<Read>().swap(p.uncorrected);
+        }
     }
-
+    lap("msa+correct round 1");
     // ---- POA round 2 on the corrected reads (correct.cpp:427-445)
     tasks.clear();
     for (auto &p : packs) {
@@ -355,6 +444,7 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
         tasks.push_back(&p.t2);
     }
     poa_run(ctx, tasks, 5, -4, -8, -6, false);
+    lap("POA round 2");
     parallel_for(nthreads, packs.size(), [&](size_t i) {
         Pack &p = packs[i];
         std::vector<std::string> msa;
@@ -366,6 +456,7 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
         p.consensus = strip_gaps(cs.consensus);
     });
 
+    lap("msa+consensus round 2");
     // ---- pack consensus headers (correct.cpp:447-470; no file labels through this entry point)
     std::vector<std::vector<Read>> consensi(n_clusters);
     for (auto &p : packs) {
@@ -378,6 +469,7 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
                                        std::string(p.consensus.size(), 'K')});
     }
 
+    std::vector<Read> consensus_set;
     // ---- clusters with several packs: third POA over the pack consensi (correct.cpp:518-538)
     std::vector<PoaTask> t3(n_clusters);
     tasks.clear();
@@ -412,9 +504,7 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
         }
     }
 
-    std::string out_c, out_u, out_s;
-    append_fastq(out_c, corrected_set);
-    append_fastq(out_u, uncorrected_set);
+    lap("third POA + headers");
     append_fastq(out_s, consensus_set);
     int rc = RTL_OK;
     auto put = [&](const std::string &s, char *buf, int64_t *len) {
@@ -429,6 +519,7 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
     put(out_c, corrected_out, corrected_len);
     put(out_u, uncorrected_out, uncorrected_len);
     put(out_s, consensi_out, consensi_len);
+    lap("output");
     ctx->stats.total_ms = now_ms() - t0;
     ctx->stats.d2h_bytes += (int64_t)(out_c.size() + out_u.size() + out_s.size());
     if (rc == RTL_ERR_CAPACITY) ctx->err = "output buffer too small (needed sizes returned in *_len)";

@@ -60,7 +60,7 @@ __host__ __device__ __forceinline__ int poa_lp(int L) { return (L + 3) & ~3; }  
 __host__ __device__ __forceinline__ int poa_ws(int L) { return poa_lp(L) + 4; }         // HF row stride (cells)
 
 template <bool WIDE>
-__global__ void __launch_bounds__(POA_T) k_poa_align(const PoaJob *__restrict__ jobs, int n_jobs,
+__global__ void __launch_bounds__(POA_T, 2) k_poa_align(const PoaJob *__restrict__ jobs, int n_jobs,
                                                      const uint8_t *__restrict__ qbytes,
                                                      const uint32_t *__restrict__ row_info,  // letter | npred<<8
                                                      const uint32_t *__restrict__ row_poff,
@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(POA_T) k_poa_align(const PoaJob *__restrict__ 
     __shared__ int s_job;
     __shared__ int s_warp[POA_T / 32], s_warp_ex[POA_T / 32];
     __shared__ int s_pl[POA_T], s_zl[POA_T];
+    __shared__ int s_hl[2][POA_T];  // H of every thread's last column, by row parity (left neighbour of the next thread)
     __shared__ int s_carry[3];  // running prefix max, P_last, Z_last of the previous chunk (or of column 0)
     __shared__ int s_pred[2][MAXP_SMEM];
     __shared__ uint32_t s_info[2], s_poff[2];
@@ -123,6 +124,18 @@ __global__ void __launch_bounds__(POA_T) k_poa_align(const PoaJob *__restrict__ 
         __syncthreads();
 
         int best = 0, bi = 0, bj = 0;
+        // Single-chunk jobs (L <= 2048) carry the previous row in registers: when a predecessor is row r-1 (the common
+        // case inside linear stretches of the graph) its H/F are never re-read from memory, and the row needs three
+        // block barriers instead of four.
+        const bool single = n_chunks == 1;
+        int pH[4], pF[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            pH[i] = 0;
+            pF[i] = NEG;
+        }
+        s_hl[0][tid] = 0;
+        __syncthreads();
 
         for (int r = 1; r <= n; ++r) {
             const int buf = r & 1;
@@ -145,11 +158,13 @@ __global__ void __launch_bounds__(POA_T) k_poa_align(const PoaJob *__restrict__ 
                 z.x = 0;
                 z.y = NEG;
                 hrow[3] = z;  // column 0
-                s_carry[0] = sg;          // prefix max over column 0: Z[0] = H[r][0] + g - 0*e
-                s_carry[1] = POA_NEGBIG;  // P of column 0 (E[r][0] = -inf)
-                s_carry[2] = sg;          // Z[0]
+                if (!single) {
+                    s_carry[0] = sg;          // prefix max over column 0: Z[0] = H[r][0] + g - 0*e
+                    s_carry[1] = POA_NEGBIG;  // P of column 0 (E[r][0] = -inf)
+                    s_carry[2] = sg;          // Z[0]
+                }
             }
-            __syncthreads();
+            if (!single) __syncthreads();
 
             for (int ch = 0; ch < n_chunks; ++ch) {
                 const int j0 = ch * POA_T * POA_CPT + tid * POA_CPT + 1;  // first of my 4 columns (1-based)
@@ -174,27 +189,42 @@ __global__ void __launch_bounds__(POA_T) k_poa_align(const PoaJob *__restrict__ 
                     sc[3] = (q4.w == letter) ? sm : sn;
                     for (int p = 0; p < np; ++p) {
                         const int prow = (p < MAXP_SMEM) ? s_pred[buf][p] : pr[poff + p];
-                        const cell_t *src = hf + (size_t)prow * Ws + (j0 + 3);
-                        cell_t c4[4];
-                        if (!WIDE) {
-                            const uint4 v = *reinterpret_cast<const uint4 *>(src);
-                            *reinterpret_cast<uint4 *>(c4) = v;
+                        int cH[4], cF[4], leftH;
+                        if (single && prow == r - 1) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                cH[i] = pH[i];
+                                cF[i] = pF[i];
+                            }
+                            leftH = (tid == 0) ? 0 : s_hl[(r - 1) & 1][tid - 1];
                         } else {
-                            const uint4 v0 = *reinterpret_cast<const uint4 *>(src);
-                            const uint4 v1 = *reinterpret_cast<const uint4 *>(src + 2);
-                            reinterpret_cast<uint4 *>(c4)[0] = v0;
-                            reinterpret_cast<uint4 *>(c4)[1] = v1;
+                            const cell_t *src = hf + (size_t)prow * Ws + (j0 + 3);
+                            cell_t c4[4];
+                            if (!WIDE) {
+                                const uint4 v = *reinterpret_cast<const uint4 *>(src);
+                                *reinterpret_cast<uint4 *>(c4) = v;
+                            } else {
+                                const uint4 v0 = *reinterpret_cast<const uint4 *>(src);
+                                const uint4 v1 = *reinterpret_cast<const uint4 *>(src + 2);
+                                reinterpret_cast<uint4 *>(c4)[0] = v0;
+                                reinterpret_cast<uint4 *>(c4)[1] = v1;
+                            }
+                            leftH = (int)src[-1].x;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                cH[i] = (int)c4[i].x;
+                                cF[i] = (int)c4[i].y;
+                            }
                         }
-                        const cell_t left = src[-1];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const int hprev = (i == 0) ? (int)left.x : (int)c4[i - 1].x;
+                            const int hprev = (i == 0) ? leftH : cH[i - 1];
                             const int d = hprev + sc[i];
                             if (d > Hd[i]) {
                                 Hd[i] = d;
                                 dp[i] = p;
                             }
-                            const int fh = (int)c4[i].x + sg, fe = (int)c4[i].y + se;
+                            const int fh = cH[i] + sg, fe = cF[i] + se;
                             const int fm = max(fh, fe);
                             if (fm > Fv[i]) {
                                 Fv[i] = fm;
@@ -235,8 +265,9 @@ __global__ void __launch_bounds__(POA_T) k_poa_align(const PoaJob *__restrict__ 
                 __syncthreads();
                 int excl = __shfl_up_sync(0xffffffffu, w, 1);
                 if (lane == 0) excl = POA_NEGBIG;
-                const int carryP = s_carry[0];
-                const int carryPl = s_carry[1], carryZl = s_carry[2];  // read before the last thread updates them
+                // column 0 (or the previous chunk): running prefix max, and P / Z of the column left of this chunk
+                const int carryP = single ? sg : s_carry[0];
+                const int carryPl = single ? POA_NEGBIG : s_carry[1], carryZl = single ? sg : s_carry[2];
                 const int Pin = max(carryP, max(s_warp_ex[wid], excl));  // max Z over all columns < j0
                 // my columns
                 int E[4], H[4], P[4];
@@ -250,6 +281,19 @@ __global__ void __launch_bounds__(POA_T) k_poa_align(const PoaJob *__restrict__ 
                 }
                 s_pl[tid] = P[3];
                 s_zl[tid] = Z[3];
+                s_hl[r & 1][tid] = H[3];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    pH[i] = H[i];
+                    pF[i] = max(Fv[i], NEG);
+                }
+                if (ch + 1 == n_chunks && r < n) {  // next row's metadata (prefetched at the start of this row)
+                    if (tid == 0) {
+                        s_info[buf ^ 1] = nx_info;
+                        s_poff[buf ^ 1] = nx_poff;
+                    }
+                    if (tid < (int)(nx_info >> 8) && tid < MAXP_SMEM) s_pred[buf ^ 1][tid] = nx_pred;
+                }
                 __syncthreads();
                 int Pl, Zl;  // left neighbour column j0-1: its prefix P and its Z
                 if (tid == 0) {
@@ -297,19 +341,12 @@ __global__ void __launch_bounds__(POA_T) k_poa_align(const PoaJob *__restrict__ 
                         *reinterpret_cast<uint4 *>(crow + (j0 - 1)) = *reinterpret_cast<const uint4 *>(k4);
                     }
                 }
-                if (tid == POA_T - 1) {
+                if (!single && tid == POA_T - 1) {
                     s_carry[0] = max(carryP, max(s_warp_ex[NW - 1], w));  // prefix incl. this chunk (w = inclusive scan)
                     s_carry[1] = P[3];
                     s_carry[2] = Z[3];
                 }
-                if (ch + 1 == n_chunks && r < n) {
-                    if (tid == 0) {
-                        s_info[buf ^ 1] = nx_info;
-                        s_poff[buf ^ 1] = nx_poff;
-                    }
-                    if (tid < (int)(nx_info >> 8) && tid < MAXP_SMEM) s_pred[buf ^ 1][tid] = nx_pred;
-                }
-                __syncthreads();
+                if (!single) __syncthreads();  // multi-chunk rows: s_carry hand-over and global H/F rows of row r-1
             }
         }
 
@@ -332,37 +369,71 @@ __global__ void __launch_bounds__(POA_T) k_poa_align(const PoaJob *__restrict__ 
             s_best[wid][2] = bj;
         }
         __syncthreads();
-        if (tid == 0) {
-            for (int wv = 1; wv < NW; ++wv) {
-                const int ob = s_best[wv][0], oi = s_best[wv][1], oj = s_best[wv][2];
-                if (ob > best || (ob == best && (oi < bi || (oi == bi && oj < bj)))) {
-                    best = ob;
-                    bi = oi;
-                    bj = oj;
+        if (wid == 0) {
+            if (lane == 0) {
+                for (int wv = 1; wv < NW; ++wv) {
+                    const int ob = s_best[wv][0], oi = s_best[wv][1], oj = s_best[wv][2];
+                    if (ob > best || (ob == best && (oi < bi || (oi == bi && oj < bj)))) {
+                        best = ob;
+                        bi = oi;
+                        bj = oj;
+                    }
                 }
             }
-            // ---- traceback (one thread; sisd_alignment_engine.cpp:527-656).  Pairs are (row or -1, query pos or -1),
-            // emitted end-to-start; the host reverses them and maps rows to node ids.
+            best = __shfl_sync(0xffffffffu, best, 0);
+            bi = __shfl_sync(0xffffffffu, bi, 0);
+            bj = __shfl_sync(0xffffffffu, bj, 0);
+            // ---- traceback (warp 0; sisd_alignment_engine.cpp:527-656).  Pairs are (row or -1, query pos or -1),
+            // emitted end-to-start; the host reverses them and maps rows to node ids.  The walk itself is serial, but
+            // most of it is a run of diagonal moves through consecutive rows: lane k speculatively fetches the code
+            // of cell (i-k, j-k) and its diagonal predecessor, and the leading lanes whose move is "diagonal to row
+            // i-k-1" are committed 32 at a time; anything else takes the general single step.
             int32_t *out = aln_out + 2 * (size_t)J.aln_off;
             int cnt = 0;
             int i = bi, j = bj;
             constexpr uint32_t PM = (1u << PB) - 1u;
             if (best > 0) {
                 while (i > 0 && j > 0) {
-                    const uint32_t c = cd[(size_t)(i - 1) * Wc + (j - 1)];
-                    const uint32_t type = c & 3u;
+                    const int ik = i - lane, jk = j - lane;
+                    const bool valid = ik >= 1 && jk >= 1;
+                    uint32_t c = 0;
+                    int prow = -1;
+                    if (valid) {
+                        c = cd[(size_t)(ik - 1) * Wc + (jk - 1)];
+                        if ((c & 3u) == 1u) prow = pr[rpoff[ik] + ((c >> 2) & PM)];
+                    }
+                    const bool chain = valid && (c & 3u) == 1u && prow == ik - 1;
+                    const unsigned m = __ballot_sync(0xffffffffu, chain);
+                    const int run = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
+                    if (lane < run) {
+                        out[2 * (cnt + lane)] = ik;
+                        out[2 * (cnt + lane) + 1] = jk - 1;
+                    }
+                    cnt += run;
+                    i -= run;
+                    j -= run;
+                    if (run == 32) continue;
+                    if (i <= 0 || j <= 0) break;
+                    // general step at (i,j): its code (and diagonal predecessor) sit in lane `run`
+                    const uint32_t c0 = __shfl_sync(0xffffffffu, c, run);
+                    const int prow0 = __shfl_sync(0xffffffffu, prow, run);
+                    const uint32_t type = c0 & 3u;
                     if (type == 0) break;
-                    const uint32_t pidx = (c >> 2) & PM;
-                    const bool ext = (c >> (2 + PB)) & 1u;
+                    const uint32_t pidx = (c0 >> 2) & PM;
+                    const bool ext = (c0 >> (2 + PB)) & 1u;
                     if (type == 1) {
-                        out[2 * cnt] = i;
-                        out[2 * cnt + 1] = j - 1;
+                        if (lane == 0) {
+                            out[2 * cnt] = i;
+                            out[2 * cnt + 1] = j - 1;
+                        }
                         ++cnt;
-                        i = pr[rpoff[i] + pidx];
+                        i = prow0;
                         j = j - 1;
                     } else if (type == 2) {
-                        out[2 * cnt] = i;
-                        out[2 * cnt + 1] = -1;
+                        if (lane == 0) {
+                            out[2 * cnt] = i;
+                            out[2 * cnt + 1] = -1;
+                        }
                         ++cnt;
                         i = pr[rpoff[i] + pidx];
                         if (ext) {  // extend_up walk
@@ -370,22 +441,28 @@ __global__ void __launch_bounds__(POA_T) k_poa_align(const PoaJob *__restrict__ 
                                 const uint32_t c2 = cd[(size_t)(i - 1) * Wc + (j - 1)];
                                 const uint32_t fpi = (c2 >> (3 + PB)) & PM;
                                 const bool stop = (c2 >> (3 + 2 * PB)) & 1u;
-                                out[2 * cnt] = i;
-                                out[2 * cnt + 1] = -1;
+                                if (lane == 0) {
+                                    out[2 * cnt] = i;
+                                    out[2 * cnt + 1] = -1;
+                                }
                                 ++cnt;
                                 i = pr[rpoff[i] + fpi];
                                 if (stop || i == 0) break;
                             }
                         }
                     } else {
-                        out[2 * cnt] = -1;
-                        out[2 * cnt + 1] = j - 1;
+                        if (lane == 0) {
+                            out[2 * cnt] = -1;
+                            out[2 * cnt + 1] = j - 1;
+                        }
                         ++cnt;
                         j = j - 1;
                         if (ext) {  // extend_left walk
                             while (true) {
-                                out[2 * cnt] = -1;
-                                out[2 * cnt + 1] = j - 1;
+                                if (lane == 0) {
+                                    out[2 * cnt] = -1;
+                                    out[2 * cnt + 1] = j - 1;
+                                }
                                 ++cnt;
                                 --j;
                                 if (j < 1) break;
@@ -396,7 +473,7 @@ __global__ void __launch_bounds__(POA_T) k_poa_align(const PoaJob *__restrict__ 
                     }
                 }
             }
-            aln_len[jb] = cnt;
+            if (lane == 0) aln_len[jb] = cnt;
         }
         __syncthreads();
     }
