@@ -14,6 +14,7 @@ struct PoaTask {
     std::vector<const char *> seq;
     std::vector<int> len;
     rtl::PoaGraph g;
+    bool acgtu = false;  // every letter is one of A,C,G,T,U (set by poa_run)
     std::vector<std::vector<std::pair<int32_t, int32_t>>> alns;  // filled when keep_alns
 };
 
