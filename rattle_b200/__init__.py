@@ -5,6 +5,12 @@ This package is the Python host-side mirror of the reference's two entry points
 `librattle_b200.so` (include/rattle_b200.h).  Everything computes on the GPU; there is no CPU fallback:
 loading fails loudly when the CUDA library has not been built, and `Context()` fails when no B200 is visible.
 """
+import os as _os
+
+# the POA engine drives up to 8 units x (1 + 4) CUDA streams; give them their own hardware queues (read by the CUDA
+# runtime when the context is created, so it must be set before the first CUDA call of the process)
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from .api import (Context, ClusterSet, RattleError, cluster_reads, correct_reads, hps_decode, hps_encode, lib_path,
                   load_library)
 

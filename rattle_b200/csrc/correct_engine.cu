@@ -397,27 +397,60 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
         packs.swap(keep);
     }
     lap("pack construction");
-    // ---- POA round 1 on the raw reads of every pack (correct.cpp:395-405)
-    std::vector<PoaTask *> tasks;
-    for (auto &p : packs) {
-        set_task(p.t1, p.creads);
-        tasks.push_back(&p.t1);
+    // ---- per-pack pipeline (correct.cpp:395-445): POA round 1 on the raw reads, MSA -> fix_msa_ends -> column vote
+    // -> corrected reads, POA round 2 on the corrected reads (length-sorted), MSA -> consensus.  Packs are
+    // independent, so they are split into units that run the whole pipeline concurrently (poa_engine.cu): while some
+    // units are in their host phases the kernels of the others keep the GPU busy.
+    {
+        CK(cudaStreamSynchronize(ctx->stream));
+        const double tp0 = now_ms();
+        const int U = poa_unit_count(ctx, packs.size());
+        const int nt = nthreads;  // the shared worker pool arbitrates between the units
+        std::vector<std::vector<Pack *>> unit(U);
+        for (size_t i = 0; i < packs.size(); ++i) unit[i % U].push_back(&packs[i]);
+        run_units(U, [&](int u) {
+            std::vector<Pack *> &mine = unit[u];
+            std::vector<PoaTask *> tasks;
+            for (Pack *p : mine) {
+                set_task(p->t1, p->creads);
+                tasks.push_back(&p->t1);
+            }
+            poa_chain(ctx, u, tasks, 5, -4, -8, -6, false, nt);
+            parallel_for(nt, mine.size(), [&](size_t i) {
+                Pack &p = *mine[i];
+                std::vector<std::string> msa;
+                p.t1.g.msa(msa);
+                p.t1.g.clear();
+                fix_msa_ends(p.creads, msa);
+                correct_pack(p.creads, msa, min_occ, gap_occ, 30.0, p.corrected, p.uncorrected);
+                append_fastq(p.fq_corrected, p.corrected);
+                append_fastq(p.fq_uncorrected, p.uncorrected);
+                p.sorted_corrected = p.corrected;
+                std::stable_sort(p.sorted_corrected.begin(), p.sorted_corrected.end(),
+                                 [](const Read &a, const Read &b) { return a.seq.size() > b.seq.size(); });  // fasta.cpp:458-464
+                std::vector<Read>().swap(p.corrected);
+                std::vector<Read>().swap(p.uncorrected);
+            });
+            tasks.clear();
+            for (Pack *p : mine) {
+                set_task(p->t2, p->sorted_corrected);
+                tasks.push_back(&p->t2);
+            }
+            poa_chain(ctx, u, tasks, 5, -4, -8, -6, false, nt);
+            parallel_for(nt, mine.size(), [&](size_t i) {
+                Pack &p = *mine[i];
+                std::vector<std::string> msa;
+                p.t2.g.msa(msa);
+                p.t2.g.clear();
+                fix_msa_ends(p.sorted_corrected, msa);
+                ColStats cs;
+                consensus_vector(p.sorted_corrected, msa, cs);
+                p.consensus = strip_gaps(cs.consensus);
+            });
+        });
+        ctx->stats.poa_wall_ms += now_ms() - tp0;
     }
-    poa_run(ctx, tasks, 5, -4, -8, -6, false);
-    lap("POA round 1");
-    parallel_for(nthreads, packs.size(), [&](size_t i) {
-        Pack &p = packs[i];
-        std::vector<std::string> msa;
-        p.t1.g.msa(msa);
-        p.t1.g.clear();
-        fix_msa_ends(p.creads, msa);
-        correct_pack(p.creads, msa, min_occ, gap_occ, 30.0, p.corrected, p.uncorrected);
-        append_fastq(p.fq_corrected, p.corrected);
-        append_fastq(p.fq_uncorrected, p.uncorrected);
-        p.sorted_corrected = p.corrected;
-        std::stable_sort(p.sorted_corrected.begin(), p.sorted_corrected.end(),
-                         [](const Read &a, const Read &b) { return a.seq.size() > b.seq.size(); });  // fasta.cpp:458-464
-    });
+    lap("POA rounds 1+2 with correction");
     // queue order = the reference's -t 1 order (correct.cpp:413-424)
     {
         size_t nc = 0, nu = out_u.size();
@@ -432,31 +465,9 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
             out_u += p.fq_uncorrected;
             std::string().swap(p.fq_corrected);
             std::string().swap(p.fq_uncorrected);
-            std::vector<Read>().swap(p.corrected);
-            std::vector<Read>().swap(p.uncorrected);
         }
     }
-    lap("msa+correct round 1");
-    // ---- POA round 2 on the corrected reads (correct.cpp:427-445)
-    tasks.clear();
-    for (auto &p : packs) {
-        set_task(p.t2, p.sorted_corrected);
-        tasks.push_back(&p.t2);
-    }
-    poa_run(ctx, tasks, 5, -4, -8, -6, false);
-    lap("POA round 2");
-    parallel_for(nthreads, packs.size(), [&](size_t i) {
-        Pack &p = packs[i];
-        std::vector<std::string> msa;
-        p.t2.g.msa(msa);
-        p.t2.g.clear();
-        fix_msa_ends(p.sorted_corrected, msa);
-        ColStats cs;
-        consensus_vector(p.sorted_corrected, msa, cs);
-        p.consensus = strip_gaps(cs.consensus);
-    });
-
-    lap("msa+consensus round 2");
+    lap("output assembly");
     // ---- pack consensus headers (correct.cpp:447-470; no file labels through this entry point)
     std::vector<std::vector<Read>> consensi(n_clusters);
     for (auto &p : packs) {
@@ -472,7 +483,7 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
     std::vector<Read> consensus_set;
     // ---- clusters with several packs: third POA over the pack consensi (correct.cpp:518-538)
     std::vector<PoaTask> t3(n_clusters);
-    tasks.clear();
+    std::vector<PoaTask *> tasks;
     for (int cid = 0; cid < n_clusters; ++cid)
         if (consensi[cid].size() > 1) {
             set_task(t3[cid], consensi[cid]);

@@ -1,12 +1,17 @@
-// Batched POA driver of hot path B: many independent partial-order alignments (one per read pack) advance in
-// lock-step — step s aligns the s-th sequence of every pack to that pack's graph on the GPU (k_poa_align, one CTA
-// per alignment), then the host threads fold the alignments into the graphs (PoaGraph::add_alignment, which also
-// re-sorts the graph) and emit the next step's graphs in rank-order CSR form.  This is the loop of
-// correct.cpp:399-402 / :430-433 / :525-528 turned inside out so that thousands of clusters share one launch.
+// Batched POA driver of hot path B.  The partial-order alignments of many read packs are independent chains
+// (read s of a pack is aligned to the graph built from reads 0..s-1: correct.cpp:399-402 / :430-433 / :525-528).
+// The packs are split into UNITS; each unit is driven by its own host thread on its own CUDA stream and slice of
+// the device arena: step s of a unit aligns the s-th sequence of every pack of the unit in one launch group
+// (one CTA per alignment), then the thread folds the alignments into the graphs (PoaGraph::add_alignment, which
+// also re-sorts the graph) and stages the next step in rank-order CSR form.  Units do not wait for each other, so
+// the kernels of some units keep the GPU busy while other units are in their host phase; callers with more host
+// work per pack (correct_engine.cu) run that work inside the unit's thread as well.
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <thread>
 
 #include "common.cuh"
@@ -16,7 +21,6 @@
 
 using namespace rtl;
 
-static double g_t_finish_wait = 0, g_t_fold = 0, g_t_stage = 0;  // RTL_TRACE phase timers
 
 enum JobKind { JK_STRIP = 0, JK_NARROW = 1, JK_WIDE = 2 };
 
@@ -25,12 +29,12 @@ struct JobRef {
     int seq_index;
     int kind;                    // JobKind
     int nst;                     // JK_STRIP: strips of 256 query columns
+    int n_spill = 0;             // JK_STRIP: rows that are also written to HBM (needed more than PS_K rows later)
     size_t hf_bytes, code_bytes; // device arena need
     int L, n;
 };
 
-// One pipeline slot: its own staging buffers, stream and half of the device arena.  While the kernel of one slot
-// runs, the host folds the alignments of the other slot into their graphs and stages that slot's next step.
+// One unit's slot: its own staging buffers, stream and slice of the device arena.
 struct PoaSlot {
     DevBuf<uint8_t> d_q;
     DevBuf<uint32_t> d_row_info, d_row_poff;
@@ -39,6 +43,9 @@ struct PoaSlot {
     DevBuf<PoaSJob> d_sjobs;
     DevBuf<uint4> d_rec;
     DevBuf<unsigned int> d_counter;
+    DevBuf<int4> d_best;
+    DevBuf<int32_t> d_spill;
+    PinBuf<int32_t> h_spill;
     PinBuf<uint8_t> h_q;
     PinBuf<uint32_t> h_row_info, h_row_poff;
     PinBuf<int32_t> h_preds, h_aln, h_aln_len;
@@ -46,33 +53,135 @@ struct PoaSlot {
     PinBuf<PoaSJob> h_sjobs;
     PinBuf<uint4> h_rec;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    unsigned char *hf = nullptr, *code = nullptr;  // this slot's arena halves
-    size_t hf_bytes = 0, code_bytes = 0;
+    static constexpr int N_SUB = 4, N_SEG_EV = 16;
+    cudaStream_t sub[N_SUB] = {nullptr, nullptr, nullptr, nullptr};  // segments of one group run side by side
+    cudaEvent_t ev_seg[N_SEG_EV] = {};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_h2d = nullptr, ev_dp = nullptr;
+    double t_submit0 = 0, t_submit1 = 0;  // host clock around the last submit (timeline trace)
+    int epoch = 0;                        // chains run on this slot so far (timeline trace)
+    unsigned char *arena = nullptr;  // this unit's slice of the device arena (score rows + traceback codes)
+    size_t arena_bytes = 0;
     std::vector<JobRef> jobs;  // in flight
     std::vector<size_t> aln_off;
     bool pending = false;
     bool keep_alns = false;
+    int n_threads = 1;                                  // host threads of the unit driving this slot
+    double t_wait = 0, t_fold = 0, t_stage = 0;         // RTL_TRACE phase timers of the running chain
+    rtl_stats st{};                                     // counters of the running chain (merged under stats_mu)
 };
 
+constexpr int POA_MAX_UNITS = 16;
+
 struct PoaState {
-    DevBuf<unsigned char> hf_arena, code_arena;
-    PoaSlot slot[2];
+    DevBuf<unsigned char> arena;
+    PoaSlot slot_store[POA_MAX_UNITS];
+    int n_units = 0;
     int occ[2] = {0, 0};
     int n_threads = 0;
+    std::mutex stats_mu;
+    cudaEvent_t ev_ref = nullptr;  // timeline trace (RTL_TRACE_FILE): device-time origin
+    double t_ref = 0;
+    FILE *trace = nullptr;
 };
 
 void poa_state_free(rtl_ctx *ctx) {
     if (ctx->poa) {
-        for (auto &sl : ctx->poa->slot) {
+        for (auto &sl : ctx->poa->slot_store) {
             if (sl.ev0) cudaEventDestroy(sl.ev0);
             if (sl.ev1) cudaEventDestroy(sl.ev1);
             if (sl.stream) cudaStreamDestroy(sl.stream);
+            for (auto &x : sl.sub)
+                if (x) cudaStreamDestroy(x);
+            for (auto &x : sl.ev_seg)
+                if (x) cudaEventDestroy(x);
+            if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
+            if (sl.ev_dp) cudaEventDestroy(sl.ev_dp);
         }
         delete ctx->poa;
     }
     ctx->poa = nullptr;
 }
+
+int host_threads();
+
+// Shared worker pool: every parallel_for of every unit thread feeds the same workers, so that the cores follow
+// the units that are in their host phase (a unit waiting for its kernel uses none).  A job is an index range with
+// an atomic cursor; the caller works on its own job too and returns when all indices are done.
+namespace {
+struct PoolJob {
+    const std::function<void(size_t)> *fn;
+    size_t n;
+    int max_workers;
+    std::atomic<size_t> next{0}, done{0};
+    std::atomic<int> workers{0};
+    std::exception_ptr err;
+    std::mutex err_mu;
+    void run_some() {
+        while (true) {
+            const size_t i = next.fetch_add(1);
+            if (i >= n) break;
+            try {
+                (*fn)(i);
+            } catch (...) {
+                std::lock_guard<std::mutex> lk(err_mu);
+                if (!err) err = std::current_exception();
+            }
+            done.fetch_add(1);
+        }
+    }
+};
+
+class WorkerPool {
+  public:
+    static WorkerPool &get() {
+        static WorkerPool *p = new WorkerPool();  // lives until process exit (workers are detached)
+        return *p;
+    }
+    void run(PoolJob &job) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            jobs_.push_back(&job);
+        }
+        cv_.notify_all();
+        job.run_some();
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            jobs_.erase(std::find(jobs_.begin(), jobs_.end(), &job));
+        }
+        // workers that took the job before it left the list are still inside run_some()
+        while (job.done.load() < job.n || job.workers.load() != 0) std::this_thread::yield();
+    }
+
+  private:
+    WorkerPool() {
+        const int n = std::max(1, host_threads() - 1);
+        for (int i = 0; i < n; ++i) std::thread([this]() { loop(); }).detach();
+    }
+    void loop() {
+        std::unique_lock<std::mutex> lk(mu_);
+        while (true) {
+            PoolJob *job = nullptr;
+            for (PoolJob *j : jobs_)
+                if (j->next.load() < j->n && j->workers.load() < j->max_workers) {
+                    job = j;
+                    break;
+                }
+            if (!job) {
+                cv_.wait_for(lk, std::chrono::milliseconds(2));
+                continue;
+            }
+            job->workers.fetch_add(1);
+            lk.unlock();
+            job->run_some();
+            job->workers.fetch_sub(1);
+            lk.lock();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::vector<PoolJob *> jobs_;
+};
+}  // namespace
 
 void parallel_for(int n_threads, size_t n, const std::function<void(size_t)> &fn) {
     if (n == 0) return;
@@ -80,18 +189,12 @@ void parallel_for(int n_threads, size_t n, const std::function<void(size_t)> &fn
         for (size_t i = 0; i < n; ++i) fn(i);
         return;
     }
-    std::atomic<size_t> next(0);
-    std::vector<std::thread> th;
-    const int nt = (int)std::min<size_t>((size_t)n_threads, n);
-    for (int t = 0; t < nt; ++t)
-        th.emplace_back([&]() {
-            while (true) {
-                size_t i = next.fetch_add(1);
-                if (i >= n) break;
-                fn(i);
-            }
-        });
-    for (auto &x : th) x.join();
+    PoolJob job;
+    job.fn = &fn;
+    job.n = n;
+    job.max_workers = n_threads - 1;  // plus the caller
+    WorkerPool::get().run(job);
+    if (job.err) std::rethrow_exception(job.err);
 }
 
 int host_threads() {
@@ -108,22 +211,34 @@ static PoaState &pstate(rtl_ctx *ctx) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&P.occ[1], k_poa_align<true>, POA_T, 0));
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        size_t budget = ctx->poa_arena_mb > 0 ? ((size_t)ctx->poa_arena_mb << 20) : std::min<size_t>(free_b * 2 / 5, 64ull << 30);
+        size_t budget = ctx->poa_arena_mb > 0 ? ((size_t)ctx->poa_arena_mb << 20) : std::min<size_t>(free_b / 2, 96ull << 30);
         budget = std::max<size_t>(budget, 64ull << 20);
-        const size_t hf_half = (budget / 3) & ~(size_t)255, code_half = (budget / 6) & ~(size_t)255;
-        P.hf_arena.need(2 * hf_half);
-        P.code_arena.need(2 * code_half);
-        for (int i = 0; i < 2; ++i) {
-            PoaSlot &sl = P.slot[i];
+        const int n_units = std::max(1, std::min(ctx->poa_units > 0 ? ctx->poa_units : 8, POA_MAX_UNITS));
+        const size_t part = (budget / n_units) & ~(size_t)255;
+        P.arena.need(n_units * part);
+        P.n_units = n_units;
+        for (int i = 0; i < n_units; ++i) {
+            PoaSlot &sl = P.slot_store[i];
             CK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
             CK(cudaEventCreate(&sl.ev0));
             CK(cudaEventCreate(&sl.ev1));
-            sl.hf = P.hf_arena.p + i * hf_half;
-            sl.code = P.code_arena.p + i * code_half;
-            sl.hf_bytes = hf_half;
-            sl.code_bytes = code_half;
+            CK(cudaEventCreate(&sl.ev_h2d));
+            CK(cudaEventCreate(&sl.ev_dp));
+            for (auto &x : sl.sub) CK(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+            for (auto &x : sl.ev_seg) CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+            sl.arena = P.arena.p + i * part;
+            sl.arena_bytes = part;
         }
+        CK(cudaFuncSetAttribute(k_poa_strip<5, -4, -8, -6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)ps_smem_bytes(PS_MAXW, PS_K)));
         P.n_threads = host_threads();
+        if (const char *tf = getenv("RTL_TRACE_FILE")) {
+            P.trace = fopen(tf, "w");
+            CK(cudaEventCreate(&P.ev_ref));
+            CK(cudaEventRecord(P.ev_ref, ctx->stream));
+            CK(cudaEventSynchronize(P.ev_ref));
+            P.t_ref = now_ms();
+        }
     }
     return *ctx->poa;
 }
@@ -170,35 +285,74 @@ static const uint8_t *letter_codes() {
     return tab;
 }
 
-// strip kernel: letter codes of the query (padded with 255 to whole strips), one 16-byte record per row
-// {letter | n_pred << 8, pred0, pred1, pred2 or offset into preds}, and the predecessor CSR for rows with > 3
-static void stage_strip_job(const JobRef &jr, PoaSJob &J, uint8_t *q, uint4 *rec, int32_t *preds) {
+// strip kernel: warps per CTA = strips per pass, passes balanced (9 strips -> 2 passes of 5 and 4, not 8 and 1)
+static int strip_warps(int nst) {
+    const int n_pass = (nst + PS_MAXW - 1) / PS_MAXW;
+    return (nst + n_pass - 1) / n_pass;
+}
+// rows of the shared-memory ring for a CTA of nw warps: 6 where the register file limits the CTAs per SM anyway,
+// 5 for 6-warp CTAs, where one row less lets a fourth CTA fit into the SM's shared memory
+static int strip_ring_rows(int nw) { return nw == 6 ? 5 : PS_K; }
+
+// strip kernel, step 1 (before the arena is divided): which rows must be spilled to HBM?  Row p is read from the
+// shared-memory ring by rows up to PS_K ranks later; if a successor is further away the row gets a spill slot
+// (slot 0 is the virtual start row).  Result: task->spill_slot[r] for r = 0..n, returns the number of spilled rows.
+static int plan_spills(PoaTask *t, int K) {
+    const PoaGraph &g = t->g;
+    const int n = g.n_nodes();
+    std::vector<int32_t> &slot = t->spill_slot;
+    slot.assign((size_t)n + 1, 0);
+    for (int r = 1; r <= n; ++r) {
+        const int v = g.rank_to_node[r - 1];
+        if (g.n_in[v] == 0) continue;  // predecessor = virtual start row = spill slot 0 unless near
+        for (int x = g.in_head[v]; x >= 0; x = g.e_next_in[x]) {
+            const int pr = g.node_to_rank[g.e_begin[x]] + 1;
+            if (r - pr > K) slot[pr] = 1;
+        }
+    }
+    int ns = 0;
+    for (int r = 1; r <= n; ++r)
+        if (slot[r]) slot[r] = ++ns;
+    return ns;
+}
+
+// strip kernel, step 2: letter codes of the query (padded with 255 to whole strips), one 16-byte record per row
+// (layout: poa_strip_kernel.cuh), the predecessor words of rows with more than 3 predecessors, and the row of
+// every spill slot (for the traceback)
+static void stage_strip_job(const JobRef &jr, PoaSJob &J, uint8_t *q, uint4 *rec, int32_t *preds, int32_t *spill_rows) {
     const PoaGraph &g = jr.task->g;
+    const std::vector<int32_t> &slot = jr.task->spill_slot;
     const uint8_t *tab = letter_codes();
     const int L = jr.L, n = jr.n;
+    const int K = strip_ring_rows(strip_warps(jr.nst));
     const char *src = jr.task->seq[jr.seq_index];
     for (int i = 0; i < L; ++i) q[i] = tab[(unsigned char)src[i]];
     memset(q + L, 255, (size_t)jr.nst * PS_STRIP - L);
     rec[0] = make_uint4(0, 0, 0, 0);
+    spill_rows[0] = 0;
     uint32_t at = 0;
     for (int r = 1; r <= n; ++r) {
         const int v = g.rank_to_node[r - 1];
         const int np = g.n_in[v];
+        if (slot[r]) spill_rows[slot[r]] = r;
         uint4 rc;
-        rc.x = (uint32_t)tab[(unsigned char)g.letter[v]] | ((uint32_t)(np == 0 ? 1 : np) << 8);
+        rc.x = (uint32_t)tab[(unsigned char)g.letter[v]] | ((uint32_t)(np == 0 ? 1 : np) << 8) | ((uint32_t)slot[r] << 16);
         rc.y = rc.z = rc.w = 0;
-        if (np <= 3) {
+        auto word = [&](int pr) -> uint32_t { return (r - pr <= K) ? (uint32_t)(r - pr) : (PS_FAR | (uint32_t)slot[pr]); };
+        if (np == 0) {
+            rc.y = word(0);
+        } else if (np <= 3) {
             uint32_t *dst = &rc.y;
             int k = 0;
-            for (int x = g.in_head[v]; x >= 0; x = g.e_next_in[x]) dst[k++] = (uint32_t)(g.node_to_rank[g.e_begin[x]] + 1);
+            for (int x = g.in_head[v]; x >= 0; x = g.e_next_in[x]) dst[k++] = word(g.node_to_rank[g.e_begin[x]] + 1);
         } else {
             rc.w = at;
             int k = 0;
             for (int x = g.in_head[v]; x >= 0; x = g.e_next_in[x], ++k) {
-                const int pr = g.node_to_rank[g.e_begin[x]] + 1;
-                preds[at++] = pr;
-                if (k == 0) rc.y = (uint32_t)pr;
-                if (k == 1) rc.z = (uint32_t)pr;
+                const uint32_t w = word(g.node_to_rank[g.e_begin[x]] + 1);
+                preds[at++] = (int32_t)w;
+                if (k == 0) rc.y = w;
+                if (k == 1) rc.z = w;
             }
         }
         rec[r] = rc;
@@ -206,6 +360,7 @@ static void stage_strip_job(const JobRef &jr, PoaSJob &J, uint8_t *q, uint4 *rec
     J.L = L;
     J.n = n;
     J.n_strips = jr.nst;
+    J.n_spill = jr.n_spill;
     J.pad = 0;
 }
 
@@ -220,7 +375,7 @@ static void submit(rtl_ctx *ctx, PoaState &P, PoaSlot &S, std::vector<JobRef> &&
     std::vector<JobRef> &jobs = S.jobs;
     cudaStream_t st = S.stream;
     const size_t nj = jobs.size();
-    auto seg_key = [](const JobRef &a) { return a.kind == JK_STRIP ? std::min(a.nst, PS_MAXW) : 100 + a.kind; };
+    auto seg_key = [](const JobRef &a) { return a.kind != JK_STRIP ? 100 + a.kind : strip_warps(a.nst); };
     std::sort(jobs.begin(), jobs.end(), [&](const JobRef &a, const JobRef &b) {
         const int ka = seg_key(a), kb = seg_key(b);
         if (ka != kb) return ka > kb;  // widest CTAs first
@@ -237,7 +392,8 @@ static void submit(rtl_ctx *ctx, PoaState &P, PoaSlot &S, std::vector<JobRef> &&
         segs.back().end = i + 1;
     }
     // offsets: strip jobs and int32-kernel jobs use separate staging arrays, one shared arena and output
-    std::vector<size_t> q_off(nj + 1, 0), row_off(nj, 0), pred_off(nj, 0), hf_off(nj + 1, 0), code_off(nj + 1, 0);
+    std::vector<size_t> q_off(nj + 1, 0), row_off(nj, 0), pred_off(nj, 0), hf_off(nj, 0), code_off(nj, 0), spill_off(nj + 1, 0);
+    size_t arena_at = 0;
     S.aln_off.assign(nj + 1, 0);
     size_t rows_old = 0, rows_strip = 0, preds_total = 0;
     for (size_t i = 0; i < nj; ++i) {
@@ -249,9 +405,13 @@ static void submit(rtl_ctx *ctx, PoaState &P, PoaSlot &S, std::vector<JobRef> &&
         pred_off[i] = preds_total;
         preds_total += jr.task->g.e_begin.size() + (size_t)jr.n;  // upper bound (sources count 1 each)
         S.aln_off[i + 1] = S.aln_off[i] + jr.n + jr.L + 8;
-        hf_off[i + 1] = hf_off[i] + ((jr.hf_bytes + 255) & ~(size_t)255);
-        code_off[i + 1] = code_off[i] + ((jr.code_bytes + 255) & ~(size_t)255);
+        hf_off[i] = arena_at;
+        arena_at += (jr.hf_bytes + 255) & ~(size_t)255;
+        code_off[i] = arena_at;
+        arena_at += (jr.code_bytes + 255) & ~(size_t)255;
+        spill_off[i + 1] = spill_off[i] + (strip ? (size_t)jr.n_spill + 1 : 0);
     }
+    if (arena_at > S.arena_bytes) throw StateError("POA group exceeds the unit's arena");
     if (q_off[nj] >= (1ull << 32) || rows_old >= (1ull << 32) || rows_strip >= (1ull << 32) ||
         preds_total >= (1ull << 32) || S.aln_off[nj] >= (1ull << 31))
         throw CapacityError("POA batch too large for 32-bit staging offsets");
@@ -259,11 +419,12 @@ static void submit(rtl_ctx *ctx, PoaState &P, PoaSlot &S, std::vector<JobRef> &&
     uint32_t *hri = S.h_row_info.need_geo(rows_old + 1);
     uint32_t *hrp = S.h_row_poff.need_geo(rows_old + 1);
     uint4 *hrec = S.h_rec.need_geo(rows_strip + 1);
+    int32_t *hsp = S.h_spill.need_geo(spill_off[nj] + 1);
     int32_t *hpr = S.h_preds.need_geo(preds_total + 1);
     PoaJob *hj = S.h_jobs.need_geo(nj);
     PoaSJob *hsj = S.h_sjobs.need_geo(nj);
     const std::vector<size_t> &aln_off = S.aln_off;
-    parallel_for(P.n_threads, nj, [&](size_t i) {
+    parallel_for(S.n_threads, nj, [&](size_t i) {
         const JobRef &jr = jobs[i];
         if (jr.kind == JK_STRIP) {
             PoaSJob &J = hsj[i];
@@ -273,7 +434,8 @@ static void submit(rtl_ctx *ctx, PoaState &P, PoaSlot &S, std::vector<JobRef> &&
             J.row_off = (uint32_t)row_off[i];
             J.pred_base = (uint32_t)pred_off[i];
             J.aln_off = (uint32_t)aln_off[i];
-            stage_strip_job(jr, J, hq + q_off[i], hrec + row_off[i], hpr + pred_off[i]);
+            J.spill_off = (uint32_t)spill_off[i];
+            stage_strip_job(jr, J, hq + q_off[i], hrec + row_off[i], hpr + pred_off[i], hsp + spill_off[i]);
         } else {
             PoaJob &J = hj[i];
             J.hf_off = hf_off[i] / (jr.kind == JK_WIDE ? 8 : 4);
@@ -294,55 +456,76 @@ static void submit(rtl_ctx *ctx, PoaState &P, PoaSlot &S, std::vector<JobRef> &&
     }
     S.d_rec.need_geo(rows_strip + 1);
     if (rows_strip) CK(cudaMemcpyAsync(S.d_rec.p, hrec, rows_strip * sizeof(uint4), cudaMemcpyHostToDevice, st));
+    S.d_spill.need_geo(spill_off[nj] + 1);
+    if (spill_off[nj]) CK(cudaMemcpyAsync(S.d_spill.p, hsp, spill_off[nj] * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(S.d_preds.need_geo(preds_total + 1), hpr, preds_total * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(S.d_jobs.need_geo(nj), hj, nj * sizeof(PoaJob), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(S.d_sjobs.need_geo(nj), hsj, nj * sizeof(PoaSJob), cudaMemcpyHostToDevice, st));
-    ctx->stats.h2d_bytes += (int64_t)(q_off[nj] + rows_old * 8 + rows_strip * 16 + preds_total * 4 +
+    S.st.h2d_bytes += (int64_t)(q_off[nj] + rows_old * 8 + rows_strip * 16 + preds_total * 4 + spill_off[nj] * 4 +
                                       nj * (sizeof(PoaJob) + sizeof(PoaSJob)));
     S.d_aln.need_geo(aln_off[nj] * 2);
     S.d_aln_len.need_geo(nj);
+    S.d_best.need_geo(nj);
     CK(cudaMemsetAsync(S.d_counter.need_geo(segs.size()), 0, 4 * segs.size(), st));
     CK(cudaEventRecord(S.ev0, st));
+    S.t_submit0 = ts0;
+    // the segments are independent: fork them over the slot's sub-streams so that the tail of one segment's
+    // kernel overlaps the others, and join before the D2H copy
+    const bool fork = segs.size() > 1 && segs.size() <= (size_t)PoaSlot::N_SEG_EV;
+    if (fork) CK(cudaEventRecord(S.ev_h2d, st));
     for (size_t si = 0; si < segs.size(); ++si) {
         const Seg &sg_ = segs[si];
+        cudaStream_t st = fork ? S.sub[si % PoaSlot::N_SUB] : S.stream;
+        if (fork) CK(cudaStreamWaitEvent(st, S.ev_h2d, 0));
         const int cnt = (int)(sg_.end - sg_.begin);
         unsigned int *counter = S.d_counter.p + si;
         if (sg_.key < 100) {
             const int nw = sg_.key;
-            const size_t smem = (size_t)nw * PS_NLET * 32 * sizeof(uint4);
+            const int K = strip_ring_rows(nw);
+            const size_t smem = ps_smem_bytes(nw, K);
             int occ = 1;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_poa_strip, nw * 32, smem));
+            auto kern = k_poa_strip<5, -4, -8, -6>;  // correct.cpp:395 createAlignmentEngine(kSW, 5, -4, -8, -6)
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nw * 32, smem));
             const int grid = (int)std::min<size_t>((size_t)cnt, (size_t)ctx->n_sm * std::max(1, occ));
-            k_poa_strip<<<grid, nw * 32, smem, st>>>(S.d_sjobs.p + sg_.begin, cnt, S.d_q.p, S.d_rec.p, S.d_preds.p,
-                                                    (uint32_t *)S.hf, (uint32_t *)S.code, S.d_aln.p,
-                                                    S.d_aln_len.p + sg_.begin, sm, sn, sg, se, counter);
+            kern<<<grid, nw * 32, smem, st>>>(S.d_sjobs.p + sg_.begin, cnt, S.d_q.p, S.d_rec.p, S.d_preds.p,
+                                              (uint32_t *)S.arena, S.d_best.p + sg_.begin, counter, K);
+            CK(cudaGetLastError());
+            k_poa_strip_traceback<<<(cnt + 3) / 4, 128, 0, st>>>(S.d_sjobs.p + sg_.begin, cnt, S.d_rec.p, S.d_preds.p,
+                                                                 S.d_spill.p, (const uint32_t *)S.arena, S.d_best.p + sg_.begin,
+                                                                 S.d_aln.p, S.d_aln_len.p + sg_.begin);
+            S.st.kernel_launches++;
         } else {
             const bool wide = sg_.key == 100 + JK_WIDE;
             const int occ = std::max(1, P.occ[wide ? 1 : 0]);
             const int grid = (int)std::min<size_t>((size_t)cnt, (size_t)ctx->n_sm * occ);
             if (!wide)
                 k_poa_align<false><<<grid, POA_T, 0, st>>>(S.d_jobs.p + sg_.begin, cnt, S.d_q.p, S.d_row_info.p,
-                                                           S.d_row_poff.p, S.d_preds.p, (short2 *)S.hf, (uint16_t *)S.code,
+                                                           S.d_row_poff.p, S.d_preds.p, (short2 *)S.arena, (uint16_t *)S.arena,
                                                            S.d_aln.p, S.d_aln_len.p + sg_.begin, sm, sn, sg, se, counter);
             else
                 k_poa_align<true><<<grid, POA_T, 0, st>>>(S.d_jobs.p + sg_.begin, cnt, S.d_q.p, S.d_row_info.p,
-                                                          S.d_row_poff.p, S.d_preds.p, (int2 *)S.hf, (uint32_t *)S.code,
+                                                          S.d_row_poff.p, S.d_preds.p, (int2 *)S.arena, (uint32_t *)S.arena,
                                                           S.d_aln.p, S.d_aln_len.p + sg_.begin, sm, sn, sg, se, counter);
         }
         CK(cudaGetLastError());
-        ctx->stats.poa_launches++;
-        ctx->stats.kernel_launches++;
+        S.st.poa_launches++;
+        S.st.kernel_launches++;
+        if (fork) {
+            CK(cudaEventRecord(S.ev_seg[si], st));
+            CK(cudaStreamWaitEvent(S.stream, S.ev_seg[si], 0));
+        }
     }
     CK(cudaEventRecord(S.ev1, st));
+    S.t_submit1 = now_ms();
     int32_t *haln = S.h_aln.need_geo(aln_off[nj] * 2);
     int32_t *hlen = S.h_aln_len.need_geo(nj);
     CK(cudaMemcpyAsync(hlen, S.d_aln_len.p, nj * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(haln, S.d_aln.p, aln_off[nj] * 8, cudaMemcpyDeviceToHost, st));
     S.pending = true;
-    ctx->stats.poa_alignments += (int64_t)nj;
-    ctx->stats.d2h_bytes += (int64_t)(aln_off[nj] * 8 + nj * 4);
-    for (size_t i = 0; i < nj; ++i) ctx->stats.poa_cells += (int64_t)jobs[i].L * jobs[i].n;
-    g_t_stage += now_ms() - ts0;
+    S.st.poa_alignments += (int64_t)nj;
+    S.st.d2h_bytes += (int64_t)(aln_off[nj] * 8 + nj * 4);
+    for (size_t i = 0; i < nj; ++i) S.st.poa_cells += (int64_t)jobs[i].L * jobs[i].n;
+    S.t_stage += now_ms() - ts0;
 }
 
 // wait for the slot's launch and fold its alignments into the graphs (host threads)
@@ -351,15 +534,15 @@ static void finish(rtl_ctx *ctx, PoaState &P, PoaSlot &S) {
     const double tw0 = now_ms();
     CK(cudaStreamSynchronize(S.stream));
     const double tw1 = now_ms();
-    g_t_finish_wait += tw1 - tw0;
+    S.t_wait += tw1 - tw0;
     S.pending = false;
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, S.ev0, S.ev1));
-    ctx->stats.poa_ms += ms;
+    S.st.poa_ms += ms;
     const int32_t *haln = S.h_aln.p;
     const int32_t *hlen = S.h_aln_len.p;
     const bool keep = S.keep_alns;
-    parallel_for(P.n_threads, S.jobs.size(), [&](size_t i) {
+    parallel_for(S.n_threads, S.jobs.size(), [&](size_t i) {
         const JobRef &jr = S.jobs[i];
         PoaGraph &g = jr.task->g;
         const int len = hlen[i];
@@ -373,111 +556,168 @@ static void finish(rtl_ctx *ctx, PoaState &P, PoaSlot &S) {
         g.add_alignment(aln, jr.task->seq[jr.seq_index], jr.L);
         if (keep) jr.task->alns[jr.seq_index] = std::move(aln);
     });
-    g_t_fold += now_ms() - tw1;
+    S.t_fold += now_ms() - tw1;
+    if (P.trace) {
+        float k0 = 0, k1 = 0;
+        cudaEventElapsedTime(&k0, P.ev_ref, S.ev0);
+        cudaEventElapsedTime(&k1, P.ev_ref, S.ev1);
+        std::lock_guard<std::mutex> lk(P.stats_mu);
+        fprintf(P.trace, "{\"unit\": %d, \"epoch\": %d, \"jobs\": %zu, \"stage0\": %.3f, \"stage1\": %.3f, \"k0\": %.3f, \"k1\": %.3f, "
+                "\"sync\": %.3f, \"fold\": %.3f}\n", (int)(&S - P.slot_store), S.epoch, S.jobs.size(), S.t_submit0 - P.t_ref,
+                S.t_submit1 - P.t_ref, k0, k1, tw1 - P.t_ref, now_ms() - P.t_ref);
+        fflush(P.trace);
+    }
     S.jobs.clear();
 }
 
-// All tasks advance in lock-step.  The tasks are split into two units that alternate between the two slots:
-// unit u's step s runs on the device while unit 1-u's step s (or s-1) is folded and re-staged on the host.
-void poa_run(rtl_ctx *ctx, std::vector<PoaTask *> &tasks, int sm, int sn, int sg, int se, bool keep_alns) {
+// One unit's chain: its tasks advance in lock-step on slot `unit`, synchronously (the calling thread is the unit's
+// driver).  n_threads = host threads this chain may use for folding/staging.
+void poa_chain(rtl_ctx *ctx, int unit, std::vector<PoaTask *> &tasks, int sm, int sn, int sg, int se, bool keep_alns,
+               int n_threads) {
     PoaState &P = pstate(ctx);
-    g_t_finish_wait = g_t_fold = g_t_stage = 0;
-    CK(cudaStreamSynchronize(ctx->stream));  // inputs produced on the ctx stream are complete
+    if (unit < 0 || unit >= P.n_units) throw StateError("poa_chain: no such unit");
+    CK(cudaSetDevice(ctx->device));
+    PoaSlot &S = P.slot_store[unit];
+    S.n_threads = std::max(1, n_threads);
+    S.t_wait = S.t_fold = S.t_stage = 0;
+    S.st = rtl_stats{};
+    S.epoch++;
+    const double t_begin = now_ms();
     size_t max_steps = 0;
+    const uint8_t *tab = letter_codes();
     for (auto *t : tasks) {
         max_steps = std::max(max_steps, t->seq.size());
         t->g.clear();
         if (keep_alns) t->alns.assign(t->seq.size(), {});
+        bool ok = true;
+        for (size_t s = 0; s < t->seq.size() && ok; ++s)
+            for (int x = 0; x < t->len[s]; ++x)
+                if (tab[(unsigned char)t->seq[s][x]] == 255) {
+                    ok = false;
+                    break;
+                }
+        t->acgtu = ok;
     }
     const int maxabs = std::max(std::max(std::abs(sm), std::abs(sn)), std::max(std::abs(sg), std::abs(se)));
-    // the int16 strip kernel assumes m > 0 > n,g,e of small magnitude (poa_strip_kernel.cuh); option poa_kernel=1
-    // forces the int32 kernel
-    const bool strip_scores = ctx->poa_kernel != 1 && sm > 0 && sn < 0 && sg < 0 && se < 0 && maxabs < 100;
-    {
-        const uint8_t *tab = letter_codes();
-        parallel_for(P.n_threads, tasks.size(), [&](size_t i) {
-            PoaTask *t = tasks[i];
-            bool ok = true;
-            for (size_t s = 0; s < t->seq.size() && ok; ++s)
-                for (int x = 0; x < t->len[s]; ++x)
-                    if (tab[(unsigned char)t->seq[s][x]] == 255) {
-                        ok = false;
-                        break;
-                    }
-            t->acgtu = ok;
-        });
-    }
-    // two units of similar total work (tasks arrive in cluster order; alternate)
-    std::vector<PoaTask *> unit[2];
-    for (size_t i = 0; i < tasks.size(); ++i) unit[tasks.size() > 1 ? (i & 1) : 0].push_back(tasks[i]);
+    // the int16 strip kernel is compiled for RATTLE's scores (correct.cpp:395: 5,-4,-8,-6); other scores take the
+    // int32 kernel, and option poa_kernel=1 forces it
+    const bool strip_scores = ctx->poa_kernel != 1 && sm == 5 && sn == -4 && sg == -8 && se == -6;
     for (size_t step = 0; step < max_steps; ++step) {
-        for (int u = 0; u < 2; ++u) {
-            PoaSlot &S = P.slot[u];
-            finish(ctx, P, S);  // step-1 of this unit
-            std::vector<JobRef> all;
-            std::vector<PoaTask *> direct;
-            for (auto *t : unit[u]) {
-                if (step >= t->seq.size()) continue;
-                const int L = t->len[step];
-                // simd_alignment_engine.cpp:652-654: empty graph or empty sequence -> empty alignment
-                if (t->g.n_nodes() == 0 || L == 0) {
-                    direct.push_back(t);
-                    continue;
-                }
-                JobRef jr;
-                jr.task = t;
-                jr.seq_index = (int)step;
-                jr.L = L;
-                jr.n = t->g.n_nodes();
-                const bool wide = t->g.max_in_degree > 32 || (int64_t)maxabs * (L + 16) >= 32000;
-                jr.kind = wide ? JK_WIDE : ((strip_scores && t->acgtu) ? JK_STRIP : JK_NARROW);
-                jr.nst = (L + PS_STRIP - 1) / PS_STRIP;
-                if (jr.kind == JK_STRIP) {
-                    jr.hf_bytes = ps_hf_words(jr.n, jr.nst) * 4;
-                    jr.code_bytes = ps_code_words(jr.n, jr.nst) * 4;
-                } else {
-                    jr.hf_bytes = (size_t)(jr.n + 1) * poa_ws(L) * (wide ? 8 : 4);
-                    jr.code_bytes = (size_t)jr.n * poa_lp(L) * (wide ? 4 : 2);
-                }
-                all.push_back(jr);
+        std::vector<JobRef> all;
+        std::vector<PoaTask *> direct;
+        for (auto *t : tasks) {
+            if (step >= t->seq.size()) continue;
+            const int L = t->len[step];
+            // simd_alignment_engine.cpp:652-654: empty graph or empty sequence -> empty alignment
+            if (t->g.n_nodes() == 0 || L == 0) {
+                direct.push_back(t);
+                continue;
             }
-            parallel_for(P.n_threads, direct.size(), [&](size_t i) {
-                PoaTask *t = direct[i];
-                t->g.add_alignment({}, t->seq[step], t->len[step]);
-            });
-            // groups that fit this slot's arena; every group but the last is completed synchronously
-            std::vector<std::vector<JobRef>> groups;
-            {
-                size_t i = 0;
-                while (i < all.size()) {
-                    std::vector<JobRef> group;
-                    size_t hf = 0, cd = 0;
-                    while (i < all.size()) {
-                        const size_t nh = hf + ((all[i].hf_bytes + 255) & ~(size_t)255);
-                        const size_t nc = cd + ((all[i].code_bytes + 255) & ~(size_t)255);
-                        if (nh > S.hf_bytes || nc > S.code_bytes) {
-                            if (group.empty())
-                                throw CapacityError("one POA alignment does not fit the device arena: raise option poa_arena_mb");
-                            break;
-                        }
-                        hf = nh;
-                        cd = nc;
-                        group.push_back(all[i++]);
-                    }
-                    groups.push_back(std::move(group));
+            JobRef jr;
+            jr.task = t;
+            jr.seq_index = (int)step;
+            jr.L = L;
+            jr.n = t->g.n_nodes();
+            const bool wide = t->g.max_in_degree > 32 || (int64_t)maxabs * (L + 16) >= 32000;
+            jr.kind = wide ? JK_WIDE : ((strip_scores && t->acgtu) ? JK_STRIP : JK_NARROW);
+            jr.nst = (L + PS_STRIP - 1) / PS_STRIP;
+            if (jr.kind == JK_STRIP) {
+                jr.hf_bytes = 0;  // after plan_spills
+                jr.code_bytes = ps_code_words(jr.n, jr.nst) * 4;
+            } else {
+                jr.hf_bytes = (size_t)(jr.n + 1) * poa_ws(L) * (wide ? 8 : 4);
+                jr.code_bytes = (size_t)jr.n * poa_lp(L) * (wide ? 4 : 2);
+            }
+            all.push_back(jr);
+        }
+        parallel_for(S.n_threads, direct.size(), [&](size_t i) {
+            PoaTask *t = direct[i];
+            t->g.add_alignment({}, t->seq[step], t->len[step]);
+        });
+        parallel_for(S.n_threads, all.size(), [&](size_t k) {
+            JobRef &jr = all[k];
+            if (jr.kind != JK_STRIP) return;
+            jr.n_spill = plan_spills(jr.task, strip_ring_rows(strip_warps(jr.nst)));
+            if (jr.n_spill >= 65535) {  // spill slots are 16-bit in the row records
+                jr.kind = JK_NARROW;
+                jr.hf_bytes = (size_t)(jr.n + 1) * poa_ws(jr.L) * 4;
+                jr.code_bytes = (size_t)jr.n * poa_lp(jr.L) * 2;
+            } else {
+                jr.hf_bytes = ps_hf_words(jr.n, jr.nst, jr.n_spill) * 4;
+            }
+        });
+        // groups that fit this unit's arena slice, one after the other
+        size_t i = 0;
+        while (i < all.size()) {
+            std::vector<JobRef> group;
+            size_t used = 0;
+            while (i < all.size()) {
+                const size_t need = used + ((all[i].hf_bytes + 255) & ~(size_t)255) + ((all[i].code_bytes + 255) & ~(size_t)255);
+                if (need > S.arena_bytes) {
+                    if (group.empty())
+                        throw CapacityError("one POA alignment does not fit the device arena: raise option poa_arena_mb");
+                    break;
                 }
+                used = need;
+                group.push_back(all[i++]);
             }
-            for (size_t gi = 0; gi < groups.size(); ++gi) {
-                submit(ctx, P, S, std::move(groups[gi]), sm, sn, sg, se, keep_alns);
-                if (gi + 1 < groups.size()) finish(ctx, P, S);
-            }
+            submit(ctx, P, S, std::move(group), sm, sn, sg, se, keep_alns);
+            finish(ctx, P, S);
         }
     }
-    finish(ctx, P, P.slot[0]);
-    finish(ctx, P, P.slot[1]);
-    if (getenv("RTL_TRACE"))
-        fprintf(stderr, "[rtl] poa_run: host waited for GPU %.1f ms, fold %.1f ms, stage+submit %.1f ms, host threads %d\n",
-                g_t_finish_wait, g_t_fold, g_t_stage, P.n_threads);
+    {
+        std::lock_guard<std::mutex> lk(P.stats_mu);
+        rtl_stats &d = ctx->stats;
+        d.h2d_bytes += S.st.h2d_bytes;
+        d.d2h_bytes += S.st.d2h_bytes;
+        d.poa_launches += S.st.poa_launches;
+        d.kernel_launches += S.st.kernel_launches;
+        d.poa_alignments += S.st.poa_alignments;
+        d.poa_cells += S.st.poa_cells;
+        d.poa_ms += S.st.poa_ms;
+        if (getenv("RTL_TRACE"))
+            fprintf(stderr, "[rtl] poa_chain unit %d: %zu tasks, %.1f ms (waited for GPU %.1f, fold %.1f, stage+submit %.1f), "
+                    "%d host threads\n", unit, tasks.size(), now_ms() - t_begin, S.t_wait, S.t_fold, S.t_stage, S.n_threads);
+    }
+}
+
+int poa_unit_count(rtl_ctx *ctx, size_t n_tasks) {
+    PoaState &P = pstate(ctx);
+    // a unit should keep a fair share of the GPU's CTA slots busy by itself
+    return (int)std::max<size_t>(1, std::min<size_t>((size_t)P.n_units, n_tasks / 48));
+}
+
+void run_units(int n_units, const std::function<void(int)> &fn) {
+    if (n_units <= 1) {
+        fn(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    std::vector<std::exception_ptr> err(n_units);
+    for (int u = 0; u < n_units; ++u)
+        th.emplace_back([&, u]() {
+            try {
+                fn(u);
+            } catch (...) {
+                err[u] = std::current_exception();
+            }
+        });
+    for (auto &x : th) x.join();
+    for (auto &e : err)
+        if (e) std::rethrow_exception(e);
+}
+
+// All tasks, split round-robin into units that run concurrently.
+void poa_run(rtl_ctx *ctx, std::vector<PoaTask *> &tasks, int sm, int sn, int sg, int se, bool keep_alns) {
+    PoaState &P = pstate(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));  // inputs produced on the ctx stream are complete
+    const double t0 = now_ms();
+    const int U = poa_unit_count(ctx, tasks.size());
+    std::vector<std::vector<PoaTask *>> unit(U);
+    for (size_t i = 0; i < tasks.size(); ++i) unit[i % U].push_back(tasks[i]);
+    const int nt = P.n_threads;  // the shared pool arbitrates between the units
+    run_units(U, [&](int u) { poa_chain(ctx, u, unit[u], sm, sn, sg, se, keep_alns, nt); });
+    ctx->stats.poa_wall_ms += now_ms() - t0;
 }
 
 int poa_msa(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, uint32_t n, int m, int nn, int g, int e,

@@ -14,11 +14,20 @@ struct PoaTask {
     std::vector<const char *> seq;
     std::vector<int> len;
     rtl::PoaGraph g;
-    bool acgtu = false;  // every letter is one of A,C,G,T,U (set by poa_run)
+    bool acgtu = false;  // every letter is one of A,C,G,T,U (set by poa_chain)
+    std::vector<int32_t> spill_slot;  // scratch of the strip kernel's staging (poa_engine.cu:plan_spills)
     std::vector<std::vector<std::pair<int32_t, int32_t>>> alns;  // filled when keep_alns
 };
 
-// Runs all tasks in lock-step on the GPU; afterwards task->g holds the final graph (call g.msa()).
+// Runs all tasks on the GPU (split into concurrently running units); afterwards task->g holds the final graph
+// (call g.msa()).
 void poa_run(rtl_ctx *ctx, std::vector<PoaTask *> &tasks, int m, int n, int g, int e, bool keep_alns);
+// The pieces of poa_run for callers that keep more per-pack host work inside the unit threads:
+// poa_unit_count = units to split n_tasks into, run_units = one thread per unit (exceptions re-thrown after join),
+// poa_chain = the synchronous chain of one unit's tasks on that unit's stream / arena slice.
+int poa_unit_count(rtl_ctx *ctx, size_t n_tasks);
+void run_units(int n_units, const std::function<void(int)> &fn);
+void poa_chain(rtl_ctx *ctx, int unit, std::vector<PoaTask *> &tasks, int m, int n, int g, int e, bool keep_alns,
+               int n_threads);
 void parallel_for(int n_threads, size_t n, const std::function<void(size_t)> &fn);
 int host_threads();

@@ -10,10 +10,14 @@
 //     hands over the row's gap carry E and its last H through a shared-memory mailbox.  There is no block
 //     barrier inside the DP; the row-wise recurrence E[j] = max(H[j-1]+g, E[j-1]+e) is a max-plus scan
 //     (3 packed steps inside the lane, 5 shuffle steps across the warp, one scalar across strips);
-//   * previous-row values stay in registers; other predecessor rows are read back by the lane that wrote them
-//     (two coalesced LDG.128 per predecessor), so H/F traffic never crosses threads;
+//   * the H/F rows of the last PS_K graph rows live in a per-warp shared-memory ring: in spoa's topological order
+//     99 % of all predecessors are at most 6 rows back (aligned siblings and short branches sit between a node and
+//     its predecessor), so predecessor rows are two LDS.128 away.  Only rows that some later row needs from
+//     further back ("spilled" rows, marked by the host) are also written to HBM — the DP's DRAM traffic is the
+//     2-byte traceback code per cell and little else;
 //   * the traceback decisions are stored as one 16-bit code per cell (as in the first kernel), built from
-//     0/1 "not equal" flags (XOR + unsigned min) that the FMA pipe packs with IMADs.
+//     0/1 "not equal" flags (XOR + unsigned min) that the FMA pipe packs with IMADs; the traceback itself is a
+//     second kernel with one warp per alignment (k_poa_strip_traceback).
 //
 // Code of cell (r, j):
 //   bit 0   H != 0                      (0 -> traceback stops here)
@@ -23,8 +27,8 @@
 //   bits 4-5  0: F[fp]+e > H[fp]+g   1: equal   2: H[fp]+g > F[fp]+e        (for the winning F predecessor)
 //   bits 6-10  fp  first predecessor (in_edges order) attaining F
 //   bits 11-15 dp  first predecessor attaining Hdiag
-// Eligibility (checked by the host, otherwise the int32 kernel runs): scores fit int16, in-degree <= 32,
-// letters within {A,C,G,T,U}, m > 0 > n,g,e.
+// Eligibility (checked by the host, otherwise the int32 kernel runs): scores 5/-4/-8/-6 that fit int16, in-degree
+// <= 32, letters within {A,C,G,T,U}, fewer than 65535 spilled rows.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,56 +36,139 @@
 namespace rtl {
 
 struct PoaSJob {
-    uint64_t hf_off;     // u32 words into the HF arena: (n+1) x n_strips x 256 words (H then F per strip), then
-                         // halo[(n+1) x n_strips] (H of the column left of the strip), then passb[n+1]
-    uint64_t code_off;   // u32 words into the code arena: n x n_strips x 128 words
+    uint64_t hf_off;     // u32 words into the arena: (n_spill+1) x n_strips x 256 words (H then F per strip) of the
+                         // spilled rows (slot 0 = virtual start row), then halo[(n_spill+1) x n_strips] (H of the
+                         // column left of the strip), then passb[n+1] (hand-over between passes)
+    uint64_t code_off;   // u32 words into the arena: n x n_strips x 128 words
     uint32_t q_off;      // bytes into the query buffer: n_strips*256 letter codes (0..4, pad 255)
     uint32_t row_off;    // into rec: n+1 entries, entry r describes row r (1-based)
-    uint32_t pred_base;  // into preds: CSR of predecessor rows (read for rows with more than 3 predecessors)
+    uint32_t pred_base;  // into preds: predecessor words of rows with more than 3 predecessors
     uint32_t aln_off;    // pairs, into the alignment output
-    int32_t L, n, n_strips, pad;
+    uint32_t spill_off;  // into spill_rows: row of every spill slot (slot 0 -> row 0)
+    int32_t L, n, n_strips, n_spill, pad;
 };
+// Row record (16 B): x = letter code | n_pred << 8 | own spill slot << 16 (0 = row is not spilled),
+// y, z, w = predecessor words (n_pred <= 3) or y, z = the first two and w = offset of the full list in preds.
+// Predecessor word: d (1..K) = the row d ranks back (in the ring), or 0x80000000 | spill slot.
 
 constexpr int PS_STRIP = 256;  // columns per warp
-constexpr int PS_D = 8;        // mailbox ring depth (rows a strip may run ahead of its right neighbour)
+constexpr int PS_D = 16;       // mailbox ring depth (rows a strip may run ahead of its right neighbour)
 constexpr int PS_MAXW = 8;     // warps per CTA (strips per pass)
 constexpr int PS_NLET = 5;     // A C G T U
+constexpr int PS_K = 6;        // graph rows kept in the shared-memory ring (upper bound; the launch picks K <= PS_K)
 constexpr int PS_NEGF = -1000; // F of the virtual start row: below every H+g, and NEGF+e stays far from int16 limits
+constexpr uint32_t PS_FAR = 0x80000000u;
 
-__host__ __device__ __forceinline__ size_t ps_hf_words(int n, int n_strips) {
-    return (size_t)(n + 1) * n_strips * 256 + (size_t)(n + 1) * n_strips + (size_t)(n + 1);
+__host__ __device__ __forceinline__ size_t ps_hf_words(int n, int n_strips, int n_spill) {
+    return (size_t)(n_spill + 1) * n_strips * 256 + (size_t)(n_spill + 1) * n_strips + (size_t)(n + 1);
 }
 __host__ __device__ __forceinline__ size_t ps_code_words(int n, int n_strips) { return (size_t)n * n_strips * 128; }
+__host__ __device__ __forceinline__ size_t ps_smem_bytes(int n_warps, int K) {
+    return (size_t)n_warps * (PS_NLET * 32 * 16 + K * 64 * 16 + 32);
+}
 
 __device__ __forceinline__ int ps_lo(uint32_t v) { return (int)(short)(v & 0xffffu); }
 __device__ __forceinline__ int ps_hi(uint32_t v) { return ((int)v) >> 16; }
-__device__ __forceinline__ uint32_t ps_pk(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
-__device__ __forceinline__ uint32_t ps_pk2(int v) { return ps_pk(v, v); }
+__host__ __device__ constexpr uint32_t ps_pk(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+__host__ __device__ constexpr uint32_t ps_pk2(int v) { return ps_pk(v, v); }
 
-// predecessor row of (row record, index) — records keep up to three predecessors inline
-__device__ __forceinline__ int ps_pred_row(const uint4 &rc, int idx, const int32_t *pr) {
-    const int np = (int)(rc.x >> 8);
-    if (idx == 0) return (int)rc.y;
-    if (idx == 1) return (int)rc.z;
-    if (np <= 3) return (int)rc.w;
-    return pr[rc.w + idx];
+// volatile shared-memory accesses by 32-bit shared-space address (keeps the mailbox addresses in one register each)
+__device__ __forceinline__ unsigned long long ps_lds64(uint32_t addr) {
+    unsigned long long v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ps_sts64(uint32_t addr, unsigned long long v) {
+    asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ int ps_lds32(uint32_t addr) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ps_sts32(uint32_t addr, int v) {
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+// predecessor word of (row record, index) — records keep up to three predecessors inline
+__device__ __forceinline__ uint32_t ps_pred_word(const uint4 &rc, int idx, const int32_t *pr) {
+    const int np = (int)((rc.x >> 8) & 0xffu);
+    if (idx == 0) return rc.y;
+    if (idx == 1) return rc.z;
+    if (np <= 3) return rc.w;
+    return (uint32_t)pr[rc.w + idx];
+}
+// ... and the row it names, seen from row r
+__device__ __forceinline__ int ps_pred_row(const uint4 &rc, int idx, const int32_t *pr, int r, const int32_t *spill_rows) {
+    const uint32_t w = ps_pred_word(rc, idx, pr);
+    return (w & PS_FAR) ? spill_rows[w & 0xffffu] : r - (int)w;
+}
+
+// One predecessor row (cH, cF = its H and F in my 8 columns, hl = its H left of the strip, lane 0 only) folded into
+// the running Hdiag / F of the current row.  FIRST: plain assignment, predecessor index 0.  Otherwise the strictly
+// better candidate replaces the running value and its index (first arg-max = the reference's in_edges order).
+template <int SG, int SE, bool FIRST>
+__device__ __forceinline__ void ps_fold_pred(const uint32_t (&cH)[4], const uint32_t (&cF)[4], int hl, bool lane0, int p,
+                                             const uint32_t (&sc)[4], uint32_t (&Hd)[4], uint32_t (&Fv)[4],
+                                             uint32_t (&fpk)[4], uint32_t (&dpk)[4]) {
+    constexpr uint32_t g2 = ps_pk2(SG), e2 = ps_pk2(SE), one2 = 0x00010001u, two2 = 0x00020002u;
+    uint32_t left = __shfl_up_sync(0xffffffffu, cH[3], 1);
+    if (lane0) left = (uint32_t)hl << 16;
+    uint32_t hprev[4];
+    hprev[0] = __byte_perm(left, cH[3], 0x5432);  // (column -1, column 3)
+    hprev[1] = cH[0];
+    hprev[2] = cH[1];
+    hprev[3] = cH[2];
+    if (FIRST) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            Hd[k] = __vadd2(hprev[k], sc[k]);
+            const uint32_t fh = __vadd2(cH[k], g2), fe = __vadd2(cF[k], e2);
+            Fv[k] = __vmaxs2(fh, fe);
+            // clamp(fh - fe, -1, 1) + 1 without a packed subtract: fh + ~fe = fh - fe - 1
+            fpk[k] = __viaddmin_s16x2_relu(__vadd2(fh, ~fe), two2, two2);
+        }
+    } else {
+        const uint32_t pp = ((uint32_t)p << 16) | (uint32_t)p, pp4 = pp << 2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t nh = __viaddmax_s16x2(hprev[k], sc[k], Hd[k]);
+            const uint32_t mh = __vminu2(nh ^ Hd[k], one2) * 0xffffu;  // strictly better -> 0xffff
+            dpk[k] = (dpk[k] & ~mh) | (pp & mh);
+            Hd[k] = nh;
+            const uint32_t fh = __vadd2(cH[k], g2), fe = __vadd2(cF[k], e2);
+            const uint32_t sf = __viaddmin_s16x2_relu(__vadd2(fh, ~fe), two2, two2);
+            const uint32_t nf = __vimax3_s16x2(fh, fe, Fv[k]);
+            const uint32_t mf = __vminu2(nf ^ Fv[k], one2) * 0xffffu;
+            fpk[k] = (fpk[k] & ~mf) | ((sf + pp4) & mf);
+            Fv[k] = nf;
+        }
+    }
+}
+
+template <int SM, int SN, int SG, int SE>
 __global__ void __launch_bounds__(PS_MAXW * 32, 3)
 k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ qcodes,
-            const uint4 *__restrict__ rec, const int32_t *__restrict__ preds, uint32_t *HF, uint32_t *codes,
-            int32_t *aln_out, int32_t *aln_len, int sm, int sn, int sg, int se, unsigned int *job_counter) {
-    extern __shared__ uint4 s_prof[];  // [warp][letter][lane] packed match/mismatch scores of the warp's strip
+            const uint4 *__restrict__ rec, const int32_t *__restrict__ preds, uint32_t *arena, int4 *best_out,
+            unsigned int *job_counter, int K) {
+    // dynamic: [warp][letter][lane] packed match/mismatch scores of the warp's strip, then [warp][PS_K][H 32 | F 32]
+    // ring of recent rows, then [warp][8] ring of H left of the strip
+    extern __shared__ uint4 s_dyn[];
     __shared__ unsigned long long s_mb[PS_MAXW][PS_D];
     __shared__ int s_done[PS_MAXW];
     __shared__ int s_job;
     __shared__ int s_best[PS_MAXW][3];
+    __shared__ uint4 s_bh[PS_MAXW * 32];  // H of the lane's best row (to find its first best column)
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int NW = blockDim.x >> 5;
-    const uint32_t g2 = ps_pk2(sg), e2 = ps_pk2(se);
-    const uint32_t one2 = 0x00010001u, two2 = 0x00020002u;
-    const int e8 = 8 * se;
+    const bool lane0 = lane == 0;
+    constexpr uint32_t g2 = ps_pk2(SG), e2 = ps_pk2(SE);
+    constexpr uint32_t one2 = 0x00010001u;
+    constexpr int e8 = 8 * SE;
+    uint4 *const prof = s_dyn + (size_t)wid * PS_NLET * 32 + lane;
+    uint4 *const ring = s_dyn + (size_t)NW * PS_NLET * 32 + (size_t)wid * K * 64 + lane;  // + idx*64 (+32 for F)
+    int *const hring = reinterpret_cast<int *>(s_dyn + (size_t)NW * (PS_NLET * 32 + K * 64)) + wid * 8;
 
     while (true) {
         if (tid == 0) s_job = (int)atomicAdd(job_counter, 1u);
@@ -91,14 +178,15 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
         if (jb >= n_jobs) break;
         const PoaSJob J = jobs[jb];
         const int n = J.n, nst = J.n_strips;
-        uint32_t *hf = HF + J.hf_off;
-        int *halo = reinterpret_cast<int *>(hf + (size_t)(n + 1) * nst * 256);
-        uint32_t *passb = reinterpret_cast<uint32_t *>(halo + (size_t)(n + 1) * nst);
-        uint32_t *cd = codes + J.code_off;
+        uint32_t *hf = arena + J.hf_off;
+        int *halo = reinterpret_cast<int *>(hf + (size_t)(J.n_spill + 1) * nst * 256);
+        uint32_t *passb = reinterpret_cast<uint32_t *>(halo + (size_t)(J.n_spill + 1) * nst);
+        uint32_t *cd = arena + J.code_off;
         const uint8_t *q = qcodes + J.q_off;
         const uint4 *recs = rec + J.row_off;
         const int32_t *pr = preds + J.pred_base;
         const int n_pass = (nst + NW - 1) / NW;
+        const uint32_t hf_stride = (uint32_t)nst * 256u, cd_stride = (uint32_t)nst * 128u;
 
         int gbv = 0, gbr = 0, gbc = 0;  // best cell of this lane over all passes: value, row, column (1-based)
 
@@ -106,108 +194,95 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
             for (int i = tid; i < PS_MAXW * PS_D; i += blockDim.x) (&s_mb[0][0])[i] = ~0ull;
             if (tid < PS_MAXW) s_done[tid] = 0;
             __syncthreads();  // also orders passb of the previous pass before its readers
-            const int t = pass * NW + wid;
+            // Strip position inside the pass: the LEFTMOST strip goes to the HIGHEST warp id.  The issue arbiter
+            // prefers high warp ids, and a strip can only wait for the strip on its left: with this order the
+            // producers run ahead (up to PS_D rows) instead of being starved by consumers that spin on them.
+            const int pos = NW - 1 - wid;
+            const int t = pass * NW + pos;
             if (t < nst) {
                 const int j0 = t * PS_STRIP + lane * 8;  // 0-based index of my first column (column j0+1)
-                uint4 *prof = s_prof + (size_t)wid * PS_NLET * 32;
                 {
                     const uint2 q8 = *reinterpret_cast<const uint2 *>(q + j0);
 #pragma unroll
                     for (int c = 0; c < PS_NLET; ++c) {
                         uint4 v;
-                        v.x = ps_pk(((q8.x) & 0xff) == (uint32_t)c ? sm : sn, ((q8.y) & 0xff) == (uint32_t)c ? sm : sn);
-                        v.y = ps_pk(((q8.x >> 8) & 0xff) == (uint32_t)c ? sm : sn, ((q8.y >> 8) & 0xff) == (uint32_t)c ? sm : sn);
-                        v.z = ps_pk(((q8.x >> 16) & 0xff) == (uint32_t)c ? sm : sn, ((q8.y >> 16) & 0xff) == (uint32_t)c ? sm : sn);
-                        v.w = ps_pk(((q8.x >> 24) & 0xff) == (uint32_t)c ? sm : sn, ((q8.y >> 24) & 0xff) == (uint32_t)c ? sm : sn);
-                        prof[c * 32 + lane] = v;
+                        v.x = ps_pk(((q8.x) & 0xff) == (uint32_t)c ? SM : SN, ((q8.y) & 0xff) == (uint32_t)c ? SM : SN);
+                        v.y = ps_pk(((q8.x >> 8) & 0xff) == (uint32_t)c ? SM : SN, ((q8.y >> 8) & 0xff) == (uint32_t)c ? SM : SN);
+                        v.z = ps_pk(((q8.x >> 16) & 0xff) == (uint32_t)c ? SM : SN, ((q8.y >> 16) & 0xff) == (uint32_t)c ? SM : SN);
+                        v.w = ps_pk(((q8.x >> 24) & 0xff) == (uint32_t)c ? SM : SN, ((q8.y >> 24) & 0xff) == (uint32_t)c ? SM : SN);
+                        prof[c * 32] = v;
                     }
                 }
-                // row 0 (virtual start): H = 0, F = -inf (sisd_alignment_engine.cpp:137-141,159-165)
-                uint32_t pH[4], pF[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    pH[k] = 0u;
-                    pF[k] = ps_pk2(PS_NEGF);
-                }
+                // row 0 (virtual start): H = 0, F = -inf (sisd_alignment_engine.cpp:137-141,159-165); it is spill
+                // slot 0 and ring entry 0
+                uint32_t *const hfs = hf + (size_t)t * 256 + lane * 4;  // my 16 bytes of H in slot 0 (F 512 B further)
+                int *const halo_s = halo + t;
                 {
-                    uint32_t *dst = hf + (size_t)t * 256 + lane * 4;
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(pH[0], pH[1], pH[2], pH[3]);
-                    *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(pF[0], pF[1], pF[2], pF[3]);
-                    if (lane == 0) halo[t] = 0;
+                    const uint4 h0 = make_uint4(0u, 0u, 0u, 0u);
+                    const uint4 f0 = make_uint4(ps_pk2(PS_NEGF), ps_pk2(PS_NEGF), ps_pk2(PS_NEGF), ps_pk2(PS_NEGF));
+                    *reinterpret_cast<uint4 *>(hfs) = h0;
+                    *reinterpret_cast<uint4 *>(hfs + 128) = f0;
+                    ring[0] = h0;
+                    ring[32] = f0;
+                    if (lane0) {
+                        halo_s[0] = 0;
+                        hring[0] = 0;
+                    }
                 }
                 __syncwarp();
-                int prevHalo = 0;  // lane 0: H[r-1][column left of the strip]
-                int cdone = 0;     // lane 31: rows the right neighbour is known to have consumed
+                uint32_t *cd_w = cd + (size_t)t * 128 + lane * 4;  // row r of the codes
+                const bool has_left = t > 0, has_right = t + 1 < nst;
+                const bool left_smem = pos > 0, right_smem = pos + 1 < NW;
+                const uint32_t mb_in = (uint32_t)__cvta_generic_to_shared(&s_mb[left_smem ? pos - 1 : 0][0]);
+                const uint32_t mb_out = (uint32_t)__cvta_generic_to_shared(&s_mb[pos][0]);
+                const uint32_t done_in = (uint32_t)__cvta_generic_to_shared(&s_done[pos]);
+                const uint32_t done_out = (uint32_t)__cvta_generic_to_shared(&s_done[right_smem ? pos + 1 : pos]);
+                const int lane_e8 = lane * e8;
+                int cdone = 0;  // lane 31: rows the right neighbour is known to have consumed
                 int bestv = 0, bestr = 0;
-                uint32_t bh[4] = {0u, 0u, 0u, 0u};
+                int idx = 0;    // ring entry of row r-1 (row r goes to idx+1 mod PS_K)
                 uint4 rc = make_uint4(0, 0, 0, 0);
                 if (n >= 1) rc = recs[1];
 
                 for (int r = 1; r <= n; ++r) {
                     const uint4 cur = rc;
                     if (r < n) rc = recs[r + 1];
-                    const int letter = (int)(cur.x & 0xffu);
-                    const int np = (int)(cur.x >> 8);
-                    const uint4 sc4 = prof[letter * 32 + lane];
+                    const int np = (int)((cur.x >> 8) & 0xffu);
+                    const uint4 sc4 = prof[(cur.x & 0xffu) * 32];
                     const uint32_t sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
                     uint32_t Hd[4], Fv[4], fpk[4], dpk[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) dpk[k] = 0u;
-
-                    for (int p = 0; p < np; ++p) {
-                        const int prow = (p == 0) ? (int)cur.y
-                                                  : (p == 1) ? (int)cur.z : ((np <= 3) ? (int)cur.w : pr[cur.w + p]);
+                    // ---- predecessors in in_edges order: ring (near) or HBM (spilled rows).  The source is chosen
+                    // by pointer (generic loads), so there is no branch around the loads: F sits 512 B after H in
+                    // both places.
+                    auto fetch = [&](uint32_t pw, uint32_t(&cH)[4], uint32_t(&cF)[4], int &hl) {
+                        const bool far = (pw & PS_FAR) != 0u;
+                        const uint32_t slot = pw & 0xffffu;
+                        int pi = idx + 1 - (int)pw;  // ring entry of row r - pw
+                        pi += (pi < 0) ? K : 0;
+                        const uint4 *src = far ? reinterpret_cast<const uint4 *>(hfs + (size_t)slot * hf_stride)
+                                               : static_cast<const uint4 *>(ring + pi * 64);
+                        const int *hsrc = far ? static_cast<const int *>(halo_s + (size_t)slot * nst)
+                                              : static_cast<const int *>(hring + pi);
+                        const uint4 h4 = src[0], f4 = src[32];
+                        hl = *hsrc;
+                        cH[0] = h4.x; cH[1] = h4.y; cH[2] = h4.z; cH[3] = h4.w;
+                        cF[0] = f4.x; cF[1] = f4.y; cF[2] = f4.z; cF[3] = f4.w;
+                    };
+                    {
                         uint32_t cH[4], cF[4];
                         int hl;
-                        if (prow == r - 1) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                cH[k] = pH[k];
-                                cF[k] = pF[k];
-                            }
-                            hl = prevHalo;
-                        } else {
-                            const uint32_t *src = hf + ((size_t)prow * nst + t) * 256 + lane * 4;
-                            const uint4 h4 = *reinterpret_cast<const uint4 *>(src);
-                            const uint4 f4 = *reinterpret_cast<const uint4 *>(src + 128);
-                            hl = (lane == 0 && t > 0) ? halo[(size_t)prow * nst + t] : 0;  // column 0 of every row is H = 0
-                            cH[0] = h4.x; cH[1] = h4.y; cH[2] = h4.z; cH[3] = h4.w;
-                            cF[0] = f4.x; cF[1] = f4.y; cF[2] = f4.z; cF[3] = f4.w;
-                        }
-                        uint32_t left = __shfl_up_sync(0xffffffffu, cH[3], 1);
-                        if (lane == 0) left = (uint32_t)hl << 16;
-                        uint32_t hprev[4];
-                        hprev[0] = __byte_perm(left, cH[3], 0x5432);  // (column -1, column 3)
-                        hprev[1] = cH[0];
-                        hprev[2] = cH[1];
-                        hprev[3] = cH[2];
-                        if (p == 0) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                Hd[k] = __vadd2(hprev[k], sc[k]);
-                                const uint32_t fh = __vadd2(cH[k], g2), fe = __vadd2(cF[k], e2);
-                                Fv[k] = __vmaxs2(fh, fe);
-                                // clamp(fh - fe, -1, 1) + 1 without a packed subtract: fh + ~fe = fh - fe - 1
-                                fpk[k] = __viaddmin_s16x2_relu(__vadd2(fh, ~fe), two2, two2);
-                            }
-                        } else {
-                            const uint32_t pp = ps_pk2(p), pp4 = ps_pk2(4 * p);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint32_t d = __vadd2(hprev[k], sc[k]);
-                                const uint32_t nh = __vmaxs2(Hd[k], d);
-                                const uint32_t mh = __vminu2(nh ^ Hd[k], one2) * 0xffffu;  // strictly better -> 0xffff
-                                dpk[k] = (dpk[k] & ~mh) | (pp & mh);
-                                Hd[k] = nh;
-                                const uint32_t fh = __vadd2(cH[k], g2), fe = __vadd2(cF[k], e2);
-                                const uint32_t fm = __vmaxs2(fh, fe);
-                                const uint32_t sf = __viaddmin_s16x2_relu(__vadd2(fh, ~fe), two2, two2);
-                                const uint32_t nf = __vmaxs2(Fv[k], fm);
-                                const uint32_t mf = __vminu2(nf ^ Fv[k], one2) * 0xffffu;
-                                fpk[k] = (fpk[k] & ~mf) | ((sf + pp4) & mf);
-                                Fv[k] = nf;
-                            }
-                        }
+                        fetch(cur.y, cH, cF, hl);
+                        ps_fold_pred<SG, SE, true>(cH, cF, hl, lane0, 0, sc, Hd, Fv, fpk, dpk);
+                    }
+#pragma unroll 1
+                    for (int p = 1; p < np; ++p) {
+                        const uint32_t pw = (p == 1) ? cur.z : ((np <= 3) ? cur.w : (uint32_t)pr[cur.w + p]);
+                        uint32_t cH[4], cF[4];
+                        int hl;
+                        fetch(pw, cH, cF, hl);
+                        ps_fold_pred<SG, SE, false>(cH, cF, hl, lane0, p, sc, Hd, Fv, fpk, dpk);
                     }
 
                     // ---- E: contribution of my own columns, warp scan, carry from the strip on the left
@@ -222,25 +297,26 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                     c = __viaddmax_s16x2(c, e2, Xg[2]);
                     c = __viaddmax_s16x2(c, e2, Xg[3]);
                     const int tlo = ps_lo(c), thi = ps_hi(c);  // columns 0-3 -> E[4], columns 4-7 -> E[8]
-                    int w = max(thi, tlo + 4 * se);
+                    int w = __viaddmax_s32(tlo, 4 * SE, thi);
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
                         const int o = __shfl_up_sync(0xffffffffu, w, d);  // lanes < d get their own w: w + d*e8 < w
-                        w = max(w, o + d * e8);
+                        w = __viaddmax_s32(o, d * e8, w);
                     }
                     const int excl = __shfl_up_sync(0xffffffffu, w, 1);
-                    int cin = sg, msgH = 0;  // strip 0: E[1] = H[r][0] + g = g
-                    if (t > 0) {
+                    int cin = SG, msgH = 0;  // strip 0: E[1] = H[r][0] + g = g
+                    if (has_left) {
                         uint32_t payload = 0;
-                        if (lane == 0) {
-                            if (wid > 0) {
-                                const volatile unsigned long long *slot = &s_mb[wid - 1][r & (PS_D - 1)];
-                                unsigned long long v;
-                                do {
-                                    v = *slot;
-                                } while ((uint32_t)(v >> 32) != (uint32_t)r);
+                        if (lane0) {
+                            if (left_smem) {
+                                const uint32_t slot = mb_in + (uint32_t)(r & (PS_D - 1)) * 8u;
+                                unsigned long long v = ps_lds64(slot);
+                                while ((uint32_t)(v >> 32) != (uint32_t)r) {
+                                    __nanosleep(40);  // leave the issue slots to the warps that produce the row
+                                    v = ps_lds64(slot);
+                                }
                                 payload = (uint32_t)v;
-                                *reinterpret_cast<volatile int *>(&s_done[wid]) = r;
+                                ps_sts32(done_in, r);
                             } else {
                                 payload = passb[r];
                             }
@@ -249,10 +325,10 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                         cin = ps_lo(payload);
                         msgH = ps_hi(payload);
                     }
-                    const int Ein = (lane == 0) ? cin : max(excl, cin + lane * e8);  // E at my first column
-                    const int E4 = max(tlo, Ein + 4 * se);
+                    const int Ein = lane0 ? cin : max(excl, cin + lane_e8);  // E at my first column
+                    const int E4 = __viaddmax_s32(Ein, 4 * SE, tlo);
                     uint32_t E[4], Ee[4], H[4];
-                    E[0] = ps_pk(Ein, E4);
+                    E[0] = __byte_perm((uint32_t)Ein, (uint32_t)E4, 0x5410);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         Ee[k] = __vadd2(E[k], e2);
@@ -264,20 +340,31 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                     for (int k = 0; k < 4; ++k) H[k] = __vmaxs2(X[k], E[k]);
 
                     // ---- hand the row over to the strip on the right: E at its first column, my last H
-                    if (t + 1 < nst && lane == 31) {
-                        const int cout = max(w, cin + 32 * e8);
-                        const uint32_t payload = ps_pk(cout, ps_hi(H[3]));
-                        if (wid + 1 < NW) {
-                            while (cdone < r - PS_D) cdone = *reinterpret_cast<volatile int *>(&s_done[wid + 1]);
-                            *reinterpret_cast<volatile unsigned long long *>(&s_mb[wid][r & (PS_D - 1)]) =
-                                ((unsigned long long)(uint32_t)r << 32) | payload;
+                    if (has_right && lane == 31) {
+                        const int cout = __viaddmax_s32(cin, 32 * e8, w);
+                        const uint32_t payload = __byte_perm((uint32_t)cout, H[3], 0x7610);
+                        if (right_smem) {
+                            while (cdone < r - PS_D) {
+                                cdone = ps_lds32(done_out);
+                                if (cdone < r - PS_D) __nanosleep(100);
+                            }
+                            ps_sts64(mb_out + (uint32_t)(r & (PS_D - 1)) * 8u, ((unsigned long long)(uint32_t)r << 32) | payload);
                         } else {
                             passb[r] = payload;
                         }
                     }
-                    if (t > 0 && lane == 0) {
-                        halo[(size_t)r * nst + t] = msgH;
-                        prevHalo = msgH;
+                    // ---- the row enters the ring (entry of row r-PS_K, which no later row reads from the ring) and,
+                    // if a row further than PS_K ahead needs it, its spill slot in HBM
+                    idx = (idx == K - 1) ? 0 : idx + 1;
+                    ring[idx * 64] = make_uint4(H[0], H[1], H[2], H[3]);
+                    ring[idx * 64 + 32] = make_uint4(Fv[0], Fv[1], Fv[2], Fv[3]);
+                    if (lane0) hring[idx] = msgH;
+                    const uint32_t myslot = cur.x >> 16;
+                    if (myslot) {
+                        uint32_t *dst = hfs + (size_t)myslot * hf_stride;
+                        *reinterpret_cast<uint4 *>(dst) = make_uint4(H[0], H[1], H[2], H[3]);
+                        *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(Fv[0], Fv[1], Fv[2], Fv[3]);
+                        if (lane0) halo_s[(size_t)myslot * nst] = msgH;
                     }
 
                     // ---- traceback codes
@@ -292,16 +379,14 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                         x = nf * 4u + x;
                         x = nee * 8u + x;
                         x = fpk[k] * 16u + x;
-                        x = dpk[k] * 2048u + x;
                         cw[k] = x;
                     }
-                    {
-                        uint32_t *dst = hf + ((size_t)r * nst + t) * 256 + lane * 4;
-                        *reinterpret_cast<uint4 *>(dst) = make_uint4(H[0], H[1], H[2], H[3]);
-                        *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(Fv[0], Fv[1], Fv[2], Fv[3]);
-                        *reinterpret_cast<uint4 *>(cd + ((size_t)(r - 1) * nst + t) * 128 + lane * 4) =
-                            make_uint4(cw[0], cw[1], cw[2], cw[3]);
+                    if (np > 1) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) cw[k] = dpk[k] * 2048u + cw[k];
                     }
+                    *reinterpret_cast<uint4 *>(cd_w) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+                    cd_w += cd_stride;
                     // ---- best cell of this lane: first row with a strictly larger H (padding columns never win:
                     // they only see mismatches and gaps, so they stay below a real cell's H)
                     uint32_t hm = __vimax3_s16x2(H[0], H[1], H[2]);
@@ -310,17 +395,14 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                     if (m > bestv) {
                         bestv = m;
                         bestr = r;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) bh[k] = H[k];
+                        s_bh[tid] = make_uint4(H[0], H[1], H[2], H[3]);
                     }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        pH[k] = H[k];
-                        pF[k] = Fv[k];
-                    }
+                    __syncwarp();  // ring entry of row r complete before the next row's reads
                 }
                 // fold this pass' best into the lane's running best: larger H, then smaller row, then smaller column
                 if (bestv > 0) {
+                    const uint4 b4 = s_bh[tid];
+                    const uint32_t bh[4] = {b4.x, b4.y, b4.z, b4.w};
                     int u = 0;
 #pragma unroll
                     for (int x = 7; x >= 0; --x) {
@@ -339,7 +421,7 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
         }
 
         // global maximum: largest H, then first row in rank order, then first column
-        // (simd_alignment_engine.cpp:1162-1167,1194-1196)
+        // (simd_alignment_engine.cpp:1162-1167,1194-1196); the traceback runs in k_poa_strip_traceback
         int best = gbv, bi = gbr, bj = gbc;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
@@ -358,7 +440,7 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
             s_best[wid][2] = bj;
         }
         __syncthreads();
-        if (wid == 0) {
+        if (tid == 0) {
             for (int wv = 1; wv < NW; ++wv) {
                 const int ob = s_best[wv][0], oi = s_best[wv][1], oj = s_best[wv][2];
                 if (ob > best || (ob == best && (oi < bi || (oi == bi && oj < bj)))) {
@@ -367,100 +449,122 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                     bj = oj;
                 }
             }
-            // ---- traceback (warp 0; sisd_alignment_engine.cpp:527-656).  Pairs are (row or -1, query pos or -1),
-            // emitted end-to-start; the host reverses them and maps rows to node ids.  Lane k speculatively
-            // fetches the code of cell (i-k, j-k); leading lanes whose move is "diagonal to row i-k-1" are
-            // committed 32 at a time, anything else takes the general single step.
-            int32_t *out = aln_out + 2 * (size_t)J.aln_off;
-            int cnt = 0;
-            int i = bi, j = bj;
-            auto code_at = [&](int row, int col) -> uint32_t {  // row >= 1, col >= 1
-                const int jj = col - 1;
-                const uint32_t wv = cd[((size_t)(row - 1) * nst + (jj >> 8)) * 128 + ((jj >> 3) & 31) * 4 + (jj & 3)];
-                return (jj & 4) ? (wv >> 16) : (wv & 0xffffu);
-            };
-            if (best > 0) {
-                while (i > 0 && j > 0) {
-                    const int ik = i - lane, jk = j - lane;
-                    const bool valid = ik >= 1 && jk >= 1;
-                    uint32_t c = 0;
-                    int prow = -1;
-                    if (valid) {
-                        c = code_at(ik, jk);
-                        const uint4 rcd = recs[ik];
-                        if ((c & 3u) == 1u) prow = ps_pred_row(rcd, (int)(c >> 11), pr);
-                    }
-                    const bool chain = valid && (c & 3u) == 1u && prow == ik - 1;
-                    const unsigned mk = __ballot_sync(0xffffffffu, chain);
-                    const int run = (mk == 0xffffffffu) ? 32 : (__ffs(~mk) - 1);
-                    if (lane < run) {
-                        out[2 * (cnt + lane)] = ik;
-                        out[2 * (cnt + lane) + 1] = jk - 1;
-                    }
-                    cnt += run;
-                    i -= run;
-                    j -= run;
-                    if (run == 32) continue;
-                    if (i <= 0 || j <= 0) break;
-                    const uint32_t c0 = __shfl_sync(0xffffffffu, c, run);
-                    const int prow0 = __shfl_sync(0xffffffffu, prow, run);
-                    if (!(c0 & 1u)) break;  // H == 0
-                    if (!(c0 & 2u)) {       // diagonal
-                        if (lane == 0) {
-                            out[2 * cnt] = i;
-                            out[2 * cnt + 1] = j - 1;
-                        }
-                        ++cnt;
-                        i = prow0;
-                        j = j - 1;
-                    } else if (!(c0 & 4u)) {  // vertical; extend_up iff H == F[p][j]+e
+            best_out[jb] = make_int4(best, bi, bj, 0);
+        }
+        // the next iteration's barriers order s_best / s_job reuse
+    }
+}
+
+// Traceback of the strip kernel's codes (sisd_alignment_engine.cpp:527-656): one WARP per alignment, so that the
+// DP kernel's CTAs are not held by this latency-bound walk.  Pairs are (row or -1, query pos or -1), emitted
+// end-to-start; the host reverses them and maps rows to node ids.  Lane k speculatively fetches the code of cell
+// (i-k, j-k); leading lanes whose move is "diagonal to row i-k-1" are committed 32 at a time, anything else takes
+// the general single step.
+__global__ void __launch_bounds__(128) k_poa_strip_traceback(const PoaSJob *__restrict__ jobs, int n_jobs,
+                                                             const uint4 *__restrict__ rec,
+                                                             const int32_t *__restrict__ preds,
+                                                             const int32_t *__restrict__ spill_rows,
+                                                             const uint32_t *__restrict__ arena,
+                                                             const int4 *__restrict__ best_in, int32_t *aln_out,
+                                                             int32_t *aln_len) {
+    const int lane = threadIdx.x & 31;
+    const int jb = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (jb >= n_jobs) return;
+    const PoaSJob J = jobs[jb];
+    const int nst = J.n_strips;
+    const uint32_t *cd = arena + J.code_off;
+    const uint4 *recs = rec + J.row_off;
+    const int32_t *pr = preds + J.pred_base;
+    const int32_t *sp = spill_rows + J.spill_off;
+    const int4 b = best_in[jb];
+    const int best = b.x;
+    int32_t *out = aln_out + 2 * (size_t)J.aln_off;
+    int cnt = 0;
+    int i = b.y, j = b.z;
+    auto code_at = [&](int row, int col) -> uint32_t {  // row >= 1, col >= 1
+        const int jj = col - 1;
+        const uint32_t wv = cd[((size_t)(row - 1) * nst + (jj >> 8)) * 128 + ((jj >> 3) & 31) * 4 + (jj & 3)];
+        return (jj & 4) ? (wv >> 16) : (wv & 0xffffu);
+    };
+    if (best > 0) {
+        while (i > 0 && j > 0) {
+            const int ik = i - lane, jk = j - lane;
+            const bool valid = ik >= 1 && jk >= 1;
+            uint32_t c = 0;
+            int prow = -1;
+            if (valid) {
+                c = code_at(ik, jk);
+                const uint4 rcd = recs[ik];
+                if ((c & 3u) == 1u) prow = ps_pred_row(rcd, (int)(c >> 11), pr, ik, sp);
+            }
+            const bool chain = valid && (c & 3u) == 1u && prow == ik - 1;
+            const unsigned mk = __ballot_sync(0xffffffffu, chain);
+            const int run = (mk == 0xffffffffu) ? 32 : (__ffs(~mk) - 1);
+            if (lane < run) {
+                out[2 * (cnt + lane)] = ik;
+                out[2 * (cnt + lane) + 1] = jk - 1;
+            }
+            cnt += run;
+            i -= run;
+            j -= run;
+            if (run == 32) continue;
+            if (i <= 0 || j <= 0) break;
+            const uint32_t c0 = __shfl_sync(0xffffffffu, c, run);
+            const int prow0 = __shfl_sync(0xffffffffu, prow, run);
+            if (!(c0 & 1u)) break;  // H == 0
+            if (!(c0 & 2u)) {       // diagonal
+                if (lane == 0) {
+                    out[2 * cnt] = i;
+                    out[2 * cnt + 1] = j - 1;
+                }
+                ++cnt;
+                i = prow0;
+                j = j - 1;
+            } else if (!(c0 & 4u)) {  // vertical; extend_up iff H == F[p][j]+e
+                if (lane == 0) {
+                    out[2 * cnt] = i;
+                    out[2 * cnt + 1] = -1;
+                }
+                ++cnt;
+                const bool ext = ((c0 >> 4) & 3u) <= 1u;
+                i = ps_pred_row(recs[i], (int)((c0 >> 6) & 31u), pr, i, sp);
+                if (ext) {
+                    while (true) {  // extend_up walk (simd_alignment_engine.cpp:1388-1425)
+                        const uint32_t c2 = code_at(i, j);
+                        const bool stop = ((c2 >> 4) & 3u) >= 1u;  // F == H[p][j]+g
                         if (lane == 0) {
                             out[2 * cnt] = i;
                             out[2 * cnt + 1] = -1;
                         }
                         ++cnt;
-                        const bool ext = ((c0 >> 4) & 3u) <= 1u;
-                        i = ps_pred_row(recs[i], (int)((c0 >> 6) & 31u), pr);
-                        if (ext) {
-                            while (true) {  // extend_up walk (simd_alignment_engine.cpp:1388-1425)
-                                const uint32_t c2 = code_at(i, j);
-                                const bool stop = ((c2 >> 4) & 3u) >= 1u;  // F == H[p][j]+g
-                                if (lane == 0) {
-                                    out[2 * cnt] = i;
-                                    out[2 * cnt + 1] = -1;
-                                }
-                                ++cnt;
-                                i = ps_pred_row(recs[i], (int)((c2 >> 6) & 31u), pr);
-                                if (stop || i == 0) break;
-                            }
-                        }
-                    } else {  // horizontal; extend_left iff H == E[j-1]+e, i.e. E[j] is an extension of E[j-1]
-                        const bool ext = (j >= 2) && !(code_at(i, j - 1) & 8u);
+                        i = ps_pred_row(recs[i], (int)((c2 >> 6) & 31u), pr, i, sp);
+                        if (stop || i == 0) break;
+                    }
+                }
+            } else {  // horizontal; extend_left iff H == E[j-1]+e, i.e. E[j] is an extension of E[j-1]
+                const bool ext = (j >= 2) && !(code_at(i, j - 1) & 8u);
+                if (lane == 0) {
+                    out[2 * cnt] = -1;
+                    out[2 * cnt + 1] = j - 1;
+                }
+                ++cnt;
+                j = j - 1;
+                if (ext) {
+                    while (true) {  // extend_left walk (simd_alignment_engine.cpp:1364-1387)
                         if (lane == 0) {
                             out[2 * cnt] = -1;
                             out[2 * cnt + 1] = j - 1;
                         }
                         ++cnt;
-                        j = j - 1;
-                        if (ext) {
-                            while (true) {  // extend_left walk (simd_alignment_engine.cpp:1364-1387)
-                                if (lane == 0) {
-                                    out[2 * cnt] = -1;
-                                    out[2 * cnt + 1] = j - 1;
-                                }
-                                ++cnt;
-                                --j;
-                                if (j < 1) break;
-                                if (code_at(i, j) & 8u) break;  // E[j+1] != E[j]+e
-                            }
-                        }
+                        --j;
+                        if (j < 1) break;
+                        if (code_at(i, j) & 8u) break;  // E[j+1] != E[j]+e
                     }
                 }
             }
-            if (lane == 0) aln_len[jb] = cnt;
         }
-        __syncthreads();
     }
+    if (lane == 0) aln_len[jb] = cnt;
 }
 
 }  // namespace rtl
