@@ -51,7 +51,7 @@ const char *rtl_last_error(const rtl_ctx *ctx); /* ctx may be NULL: error of the
 /* Tunables (all optional): "wave" = candidate seeds evaluated per greedy wave (default 512),
  * "task_cap" = candidate-pair buffer entries, "scratch_mb" = match scratch for oversized pairs,
  * "poa_arena_mb" = device memory for POA score rows + traceback codes, "poa_units" = concurrently running POA
- * units (default 8; both set before the first POA call), "poa_kernel" = 1 forces the int32 POA kernel.
+ * units (default 12; both set before the first POA call), "poa_kernel" = 1 forces the int32 POA kernel.
  * Returns RTL_ERR_INPUT for an unknown key. */
 int rtl_set_option(rtl_ctx *ctx, const char *key, int64_t value);
 
@@ -80,6 +80,8 @@ typedef struct {
     double total_ms;         /* host wall time of the call */
     double poa_wall_ms;      /* host wall time inside the POA phases (kernels of concurrent units overlap, so
                                 poa_ms, the sum of their device times, can exceed it) */
+    double poa_busy_ms;      /* device time with at least one POA launch group running (union of the groups'
+                                CUDA-event intervals): the denominator of the POA roofline */
 } rtl_stats;
 int rtl_get_stats(const rtl_ctx *ctx, rtl_stats *out);
 

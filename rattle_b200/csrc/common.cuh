@@ -124,7 +124,7 @@ struct rtl_ctx {
     int64_t task_cap = 32ll << 20;
     int64_t scratch_mb = 1024;
     int poa_batch = 0;
-    int poa_units = 0;         // 0 = 8 concurrently running units (set before the first POA call)
+    int poa_units = 0;         // 0 = 12 concurrently running units (set before the first POA call)
     int poa_kernel = 0;        // 0 = int16 strip kernel where eligible, 1 = int32 kernel only
     int64_t poa_arena_mb = 0;  // 0 = 40 % of free device memory, at most 64 GB
     // sharding

@@ -449,6 +449,7 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
             });
         });
         ctx->stats.poa_wall_ms += now_ms() - tp0;
+        poa_account_busy(ctx);
     }
     lap("POA rounds 1+2 with correction");
     // queue order = the reference's -t 1 order (correct.cpp:413-424)

@@ -79,9 +79,10 @@ struct PoaState {
     int occ[2] = {0, 0};
     int n_threads = 0;
     std::mutex stats_mu;
-    cudaEvent_t ev_ref = nullptr;  // timeline trace (RTL_TRACE_FILE): device-time origin
+    cudaEvent_t ev_ref = nullptr;  // device-time origin of the kernel intervals below
     double t_ref = 0;
-    FILE *trace = nullptr;
+    FILE *trace = nullptr;         // RTL_TRACE_FILE: one JSON line per launch group (tools/timeline.py)
+    std::vector<std::pair<float, float>> intervals;  // [first kernel start, last kernel end] of every launch group
 };
 
 void poa_state_free(rtl_ctx *ctx) {
@@ -213,7 +214,7 @@ static PoaState &pstate(rtl_ctx *ctx) {
         CK(cudaMemGetInfo(&free_b, &total_b));
         size_t budget = ctx->poa_arena_mb > 0 ? ((size_t)ctx->poa_arena_mb << 20) : std::min<size_t>(free_b / 2, 96ull << 30);
         budget = std::max<size_t>(budget, 64ull << 20);
-        const int n_units = std::max(1, std::min(ctx->poa_units > 0 ? ctx->poa_units : 8, POA_MAX_UNITS));
+        const int n_units = std::max(1, std::min(ctx->poa_units > 0 ? ctx->poa_units : 12, POA_MAX_UNITS));
         const size_t part = (budget / n_units) & ~(size_t)255;
         P.arena.need(n_units * part);
         P.n_units = n_units;
@@ -232,13 +233,11 @@ static PoaState &pstate(rtl_ctx *ctx) {
         CK(cudaFuncSetAttribute(k_poa_strip<5, -4, -8, -6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)ps_smem_bytes(PS_MAXW, PS_K)));
         P.n_threads = host_threads();
-        if (const char *tf = getenv("RTL_TRACE_FILE")) {
-            P.trace = fopen(tf, "w");
-            CK(cudaEventCreate(&P.ev_ref));
-            CK(cudaEventRecord(P.ev_ref, ctx->stream));
-            CK(cudaEventSynchronize(P.ev_ref));
-            P.t_ref = now_ms();
-        }
+        if (const char *tf = getenv("RTL_TRACE_FILE")) P.trace = fopen(tf, "w");
+        CK(cudaEventCreate(&P.ev_ref));
+        CK(cudaEventRecord(P.ev_ref, ctx->stream));
+        CK(cudaEventSynchronize(P.ev_ref));
+        P.t_ref = now_ms();
     }
     return *ctx->poa;
 }
@@ -557,15 +556,18 @@ static void finish(rtl_ctx *ctx, PoaState &P, PoaSlot &S) {
         if (keep) jr.task->alns[jr.seq_index] = std::move(aln);
     });
     S.t_fold += now_ms() - tw1;
-    if (P.trace) {
+    {
         float k0 = 0, k1 = 0;
         cudaEventElapsedTime(&k0, P.ev_ref, S.ev0);
         cudaEventElapsedTime(&k1, P.ev_ref, S.ev1);
         std::lock_guard<std::mutex> lk(P.stats_mu);
+        P.intervals.emplace_back(k0, k1);
+        if (P.trace) {
         fprintf(P.trace, "{\"unit\": %d, \"epoch\": %d, \"jobs\": %zu, \"stage0\": %.3f, \"stage1\": %.3f, \"k0\": %.3f, \"k1\": %.3f, "
                 "\"sync\": %.3f, \"fold\": %.3f}\n", (int)(&S - P.slot_store), S.epoch, S.jobs.size(), S.t_submit0 - P.t_ref,
                 S.t_submit1 - P.t_ref, k0, k1, tw1 - P.t_ref, now_ms() - P.t_ref);
-        fflush(P.trace);
+            fflush(P.trace);
+        }
     }
     S.jobs.clear();
 }
@@ -681,6 +683,28 @@ void poa_chain(rtl_ctx *ctx, int unit, std::vector<PoaTask *> &tasks, int sm, in
     }
 }
 
+// device time during which at least one POA launch group was running since the last call (union of the groups'
+// [start, end] intervals, CUDA events); added to stats.poa_busy_ms
+void poa_account_busy(rtl_ctx *ctx) {
+    PoaState &P = pstate(ctx);
+    std::lock_guard<std::mutex> lk(P.stats_mu);
+    std::sort(P.intervals.begin(), P.intervals.end());
+    double busy = 0;
+    float cur_a = 0, cur_b = -1;
+    for (auto &iv : P.intervals) {
+        if (cur_b < cur_a || iv.first > cur_b) {
+            if (cur_b >= cur_a) busy += cur_b - cur_a;
+            cur_a = iv.first;
+            cur_b = iv.second;
+        } else if (iv.second > cur_b) {
+            cur_b = iv.second;
+        }
+    }
+    if (cur_b >= cur_a) busy += cur_b - cur_a;
+    P.intervals.clear();
+    ctx->stats.poa_busy_ms += busy;
+}
+
 int poa_unit_count(rtl_ctx *ctx, size_t n_tasks) {
     PoaState &P = pstate(ctx);
     // a unit should keep a fair share of the GPU's CTA slots busy by itself
@@ -718,6 +742,7 @@ void poa_run(rtl_ctx *ctx, std::vector<PoaTask *> &tasks, int sm, int sn, int sg
     const int nt = P.n_threads;  // the shared pool arbitrates between the units
     run_units(U, [&](int u) { poa_chain(ctx, u, unit[u], sm, sn, sg, se, keep_alns, nt); });
     ctx->stats.poa_wall_ms += now_ms() - t0;
+    poa_account_busy(ctx);
 }
 
 int poa_msa(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, uint32_t n, int m, int nn, int g, int e,

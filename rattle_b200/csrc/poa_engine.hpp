@@ -26,6 +26,7 @@ void poa_run(rtl_ctx *ctx, std::vector<PoaTask *> &tasks, int m, int n, int g, i
 // poa_unit_count = units to split n_tasks into, run_units = one thread per unit (exceptions re-thrown after join),
 // poa_chain = the synchronous chain of one unit's tasks on that unit's stream / arena slice.
 int poa_unit_count(rtl_ctx *ctx, size_t n_tasks);
+void poa_account_busy(rtl_ctx *ctx);  // folds the launch intervals since the last call into stats.poa_busy_ms
 void run_units(int n_units, const std::function<void(int)> &fn);
 void poa_chain(rtl_ctx *ctx, int unit, std::vector<PoaTask *> &tasks, int m, int n, int g, int e, bool keep_alns,
                int n_threads);

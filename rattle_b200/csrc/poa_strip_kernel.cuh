@@ -38,7 +38,8 @@ namespace rtl {
 struct PoaSJob {
     uint64_t hf_off;     // u32 words into the arena: (n_spill+1) x n_strips x 256 words (H then F per strip) of the
                          // spilled rows (slot 0 = virtual start row), then halo[(n_spill+1) x n_strips] (H of the
-                         // column left of the strip), then passb[n+1] (hand-over between passes)
+                         // column left of the strip), then passb[n+1] (hand-over between passes), then 8 words per
+                         // thread: H of the lane's best row and its best cell over all passes (value, row, column)
     uint64_t code_off;   // u32 words into the arena: n x n_strips x 128 words
     uint32_t q_off;      // bytes into the query buffer: n_strips*256 letter codes (0..4, pad 255)
     uint32_t row_off;    // into rec: n+1 entries, entry r describes row r (1-based)
@@ -60,7 +61,8 @@ constexpr int PS_NEGF = -1000; // F of the virtual start row: below every H+g, a
 constexpr uint32_t PS_FAR = 0x80000000u;
 
 __host__ __device__ __forceinline__ size_t ps_hf_words(int n, int n_strips, int n_spill) {
-    return (size_t)(n_spill + 1) * n_strips * 256 + (size_t)(n_spill + 1) * n_strips + (size_t)(n + 1);
+    return (size_t)(n_spill + 1) * n_strips * 256 + (size_t)(n_spill + 1) * n_strips + (size_t)((n + 1 + 3) & ~3) +
+           (size_t)PS_MAXW * 32 * 8;
 }
 __host__ __device__ __forceinline__ size_t ps_code_words(int n, int n_strips) { return (size_t)n * n_strips * 128; }
 __host__ __device__ __forceinline__ size_t ps_smem_bytes(int n_warps, int K) {
@@ -88,6 +90,34 @@ __device__ __forceinline__ int ps_lds32(uint32_t addr) {
 }
 __device__ __forceinline__ void ps_sts32(uint32_t addr, int v) {
     asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// H (4 words), F (4 words, 512 B further) and the halo word of one predecessor row: from the shared-memory ring
+// (32-bit shared addresses) or, for a spilled row, from HBM — predicated loads into the same registers, no branch.
+__device__ __forceinline__ void ps_fetch_row(bool far, uint32_t s_row, uint32_t s_halo, const uint32_t *g_row,
+                                             const int *g_halo, uint32_t (&cH)[4], uint32_t (&cF)[4], int &hl) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pf;\n\t"
+        "setp.ne.u32 pf, %9, 0;\n\t"
+        "@pf ld.global.v4.u32 {%0,%1,%2,%3}, [%12];\n\t"
+        "@pf ld.global.v4.u32 {%4,%5,%6,%7}, [%12+512];\n\t"
+        "@pf ld.global.s32 %8, [%13];\n\t"
+        "@!pf ld.shared.v4.u32 {%0,%1,%2,%3}, [%10];\n\t"
+        "@!pf ld.shared.v4.u32 {%4,%5,%6,%7}, [%10+512];\n\t"
+        "@!pf ld.shared.s32 %8, [%11];\n\t"
+        "}"
+        : "=r"(cH[0]), "=r"(cH[1]), "=r"(cH[2]), "=r"(cH[3]), "=r"(cF[0]), "=r"(cF[1]), "=r"(cF[2]), "=r"(cF[3]), "=r"(hl)
+        : "r"((uint32_t)far), "r"(s_row), "r"(s_halo), "l"(g_row), "l"(g_halo)
+        : "memory");
+}
+__device__ __forceinline__ void ps_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ps_lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 // predecessor word of (row record, index) — records keep up to three predecessors inline
@@ -158,7 +188,6 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
     __shared__ int s_done[PS_MAXW];
     __shared__ int s_job;
     __shared__ int s_best[PS_MAXW][3];
-    __shared__ uint4 s_bh[PS_MAXW * 32];  // H of the lane's best row (to find its first best column)
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int NW = blockDim.x >> 5;
@@ -166,9 +195,11 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
     constexpr uint32_t g2 = ps_pk2(SG), e2 = ps_pk2(SE);
     constexpr uint32_t one2 = 0x00010001u;
     constexpr int e8 = 8 * SE;
-    uint4 *const prof = s_dyn + (size_t)wid * PS_NLET * 32 + lane;
-    uint4 *const ring = s_dyn + (size_t)NW * PS_NLET * 32 + (size_t)wid * K * 64 + lane;  // + idx*64 (+32 for F)
-    int *const hring = reinterpret_cast<int *>(s_dyn + (size_t)NW * (PS_NLET * 32 + K * 64)) + wid * 8;
+    // 32-bit shared-space addresses (one register each, no generic-address arithmetic in the row loop)
+    const uint32_t dyn_s = (uint32_t)__cvta_generic_to_shared(s_dyn);
+    const uint32_t prof_s = dyn_s + (uint32_t)((wid * PS_NLET * 32 + lane) * 16);             // + letter*512
+    const uint32_t ring_s = dyn_s + (uint32_t)((NW * PS_NLET * 32 + wid * K * 64 + lane) * 16);  // + idx*1024 (F +512)
+    const uint32_t hring_s = dyn_s + (uint32_t)(NW * (PS_NLET * 32 + K * 64) * 16 + wid * 32);   // + idx*4
 
     while (true) {
         if (tid == 0) s_job = (int)atomicAdd(job_counter, 1u);
@@ -178,17 +209,18 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
         if (jb >= n_jobs) break;
         const PoaSJob J = jobs[jb];
         const int n = J.n, nst = J.n_strips;
-        uint32_t *hf = arena + J.hf_off;
-        int *halo = reinterpret_cast<int *>(hf + (size_t)(J.n_spill + 1) * nst * 256);
-        uint32_t *passb = reinterpret_cast<uint32_t *>(halo + (size_t)(J.n_spill + 1) * nst);
+        uint32_t *hf = arena + J.hf_off;  // word offsets below are relative to hf (a job's region is far below 16 GB)
+        const uint32_t halo_o = (uint32_t)(J.n_spill + 1) * (uint32_t)nst * 256u;
+        const uint32_t passb_o = (halo_o + (uint32_t)(J.n_spill + 1) * (uint32_t)nst + 3u) & ~3u;
+        uint32_t *const mine = hf + ((passb_o + (uint32_t)((n + 1 + 3) & ~3)) + (uint32_t)tid * 8u);  // [0..3] best-row H, [4..6] best cell
         uint32_t *cd = arena + J.code_off;
         const uint8_t *q = qcodes + J.q_off;
         const uint4 *recs = rec + J.row_off;
-        const int32_t *pr = preds + J.pred_base;
+        const uint32_t pred_base = J.pred_base;
         const int n_pass = (nst + NW - 1) / NW;
         const uint32_t hf_stride = (uint32_t)nst * 256u, cd_stride = (uint32_t)nst * 128u;
 
-        int gbv = 0, gbr = 0, gbc = 0;  // best cell of this lane over all passes: value, row, column (1-based)
+        *reinterpret_cast<uint4 *>(mine + 4) = make_uint4(0u, 0u, 0u, 0u);
 
         for (int pass = 0; pass < n_pass; ++pass) {
             for (int i = tid; i < PS_MAXW * PS_D; i += blockDim.x) (&s_mb[0][0])[i] = ~0ull;
@@ -210,23 +242,23 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                         v.y = ps_pk(((q8.x >> 8) & 0xff) == (uint32_t)c ? SM : SN, ((q8.y >> 8) & 0xff) == (uint32_t)c ? SM : SN);
                         v.z = ps_pk(((q8.x >> 16) & 0xff) == (uint32_t)c ? SM : SN, ((q8.y >> 16) & 0xff) == (uint32_t)c ? SM : SN);
                         v.w = ps_pk(((q8.x >> 24) & 0xff) == (uint32_t)c ? SM : SN, ((q8.y >> 24) & 0xff) == (uint32_t)c ? SM : SN);
-                        prof[c * 32] = v;
+                        ps_sts128(prof_s + c * 512, v.x, v.y, v.z, v.w);
                     }
                 }
                 // row 0 (virtual start): H = 0, F = -inf (sisd_alignment_engine.cpp:137-141,159-165); it is spill
                 // slot 0 and ring entry 0
-                uint32_t *const hfs = hf + (size_t)t * 256 + lane * 4;  // my 16 bytes of H in slot 0 (F 512 B further)
-                int *const halo_s = halo + t;
+                const uint32_t hfs_o = (uint32_t)t * 256u + (uint32_t)lane * 4u;  // my 16 bytes of H in slot 0 (F 512 B further)
+                const uint32_t halo_so = halo_o + (uint32_t)t;
                 {
                     const uint4 h0 = make_uint4(0u, 0u, 0u, 0u);
                     const uint4 f0 = make_uint4(ps_pk2(PS_NEGF), ps_pk2(PS_NEGF), ps_pk2(PS_NEGF), ps_pk2(PS_NEGF));
-                    *reinterpret_cast<uint4 *>(hfs) = h0;
-                    *reinterpret_cast<uint4 *>(hfs + 128) = f0;
-                    ring[0] = h0;
-                    ring[32] = f0;
+                    *reinterpret_cast<uint4 *>(hf + hfs_o) = h0;
+                    *reinterpret_cast<uint4 *>(hf + hfs_o + 128) = f0;
+                    ps_sts128(ring_s, h0.x, h0.y, h0.z, h0.w);
+                    ps_sts128(ring_s + 512, f0.x, f0.y, f0.z, f0.w);
                     if (lane0) {
-                        halo_s[0] = 0;
-                        hring[0] = 0;
+                        hf[halo_so] = 0u;
+                        ps_sts32(hring_s, 0);
                     }
                 }
                 __syncwarp();
@@ -238,7 +270,7 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                 const uint32_t done_in = (uint32_t)__cvta_generic_to_shared(&s_done[pos]);
                 const uint32_t done_out = (uint32_t)__cvta_generic_to_shared(&s_done[right_smem ? pos + 1 : pos]);
                 const int lane_e8 = lane * e8;
-                int cdone = 0;  // lane 31: rows the right neighbour is known to have consumed
+                int cdone = 0;  // rows the right neighbour is known to have consumed
                 int bestv = 0, bestr = 0;
                 int idx = 0;    // ring entry of row r-1 (row r goes to idx+1 mod PS_K)
                 uint4 rc = make_uint4(0, 0, 0, 0);
@@ -248,27 +280,19 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                     const uint4 cur = rc;
                     if (r < n) rc = recs[r + 1];
                     const int np = (int)((cur.x >> 8) & 0xffu);
-                    const uint4 sc4 = prof[(cur.x & 0xffu) * 32];
+                    const uint4 sc4 = ps_lds128(prof_s + (cur.x & 0xffu) * 512u);
                     const uint32_t sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
                     uint32_t Hd[4], Fv[4], fpk[4], dpk[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) dpk[k] = 0u;
-                    // ---- predecessors in in_edges order: ring (near) or HBM (spilled rows).  The source is chosen
-                    // by pointer (generic loads), so there is no branch around the loads: F sits 512 B after H in
-                    // both places.
+                    // ---- predecessors in in_edges order: ring (near) or HBM (spilled rows), predicated loads
                     auto fetch = [&](uint32_t pw, uint32_t(&cH)[4], uint32_t(&cF)[4], int &hl) {
                         const bool far = (pw & PS_FAR) != 0u;
                         const uint32_t slot = pw & 0xffffu;
-                        int pi = idx + 1 - (int)pw;  // ring entry of row r - pw
+                        int pi = idx + 1 - (int)(pw & 0xffu);  // ring entry of row r - pw
                         pi += (pi < 0) ? K : 0;
-                        const uint4 *src = far ? reinterpret_cast<const uint4 *>(hfs + (size_t)slot * hf_stride)
-                                               : static_cast<const uint4 *>(ring + pi * 64);
-                        const int *hsrc = far ? static_cast<const int *>(halo_s + (size_t)slot * nst)
-                                              : static_cast<const int *>(hring + pi);
-                        const uint4 h4 = src[0], f4 = src[32];
-                        hl = *hsrc;
-                        cH[0] = h4.x; cH[1] = h4.y; cH[2] = h4.z; cH[3] = h4.w;
-                        cF[0] = f4.x; cF[1] = f4.y; cF[2] = f4.z; cF[3] = f4.w;
+                        ps_fetch_row(far, ring_s + (uint32_t)pi * 1024u, hring_s + (uint32_t)pi * 4u,
+                                     hf + (hfs_o + slot * hf_stride), reinterpret_cast<const int *>(hf + (halo_so + slot * (uint32_t)nst)), cH, cF, hl);
                     };
                     {
                         uint32_t cH[4], cF[4];
@@ -278,7 +302,7 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                     }
 #pragma unroll 1
                     for (int p = 1; p < np; ++p) {
-                        const uint32_t pw = (p == 1) ? cur.z : ((np <= 3) ? cur.w : (uint32_t)pr[cur.w + p]);
+                        const uint32_t pw = (p == 1) ? cur.z : ((np <= 3) ? cur.w : (uint32_t)preds[pred_base + cur.w + p]);
                         uint32_t cH[4], cF[4];
                         int hl;
                         fetch(pw, cH, cF, hl);
@@ -306,22 +330,21 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                     const int excl = __shfl_up_sync(0xffffffffu, w, 1);
                     int cin = SG, msgH = 0;  // strip 0: E[1] = H[r][0] + g = g
                     if (has_left) {
-                        uint32_t payload = 0;
-                        if (lane0) {
-                            if (left_smem) {
-                                const uint32_t slot = mb_in + (uint32_t)(r & (PS_D - 1)) * 8u;
-                                unsigned long long v = ps_lds64(slot);
-                                while ((uint32_t)(v >> 32) != (uint32_t)r) {
-                                    __nanosleep(40);  // leave the issue slots to the warps that produce the row
-                                    v = ps_lds64(slot);
-                                }
-                                payload = (uint32_t)v;
-                                ps_sts32(done_in, r);
-                            } else {
-                                payload = passb[r];
+                        // every lane polls the same word (broadcast read): no divergence, no shuffle
+                        uint32_t payload;
+                        if (left_smem) {
+                            const uint32_t slot = mb_in + (uint32_t)(r & (PS_D - 1)) * 8u;
+                            unsigned long long v = ps_lds64(slot);
+                            while ((uint32_t)(v >> 32) != (uint32_t)r) {
+                                __nanosleep(40);  // leave the issue slots to the warps that produce the row
+                                v = ps_lds64(slot);
                             }
+                            payload = (uint32_t)v;
+                            __syncwarp();  // all lanes have read the slot before the producer may reuse it
+                            if (lane0) ps_sts32(done_in, r);
+                        } else {
+                            payload = hf[passb_o + (uint32_t)r];
                         }
-                        payload = __shfl_sync(0xffffffffu, payload, 0);
                         cin = ps_lo(payload);
                         msgH = ps_hi(payload);
                     }
@@ -340,31 +363,32 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                     for (int k = 0; k < 4; ++k) H[k] = __vmaxs2(X[k], E[k]);
 
                     // ---- hand the row over to the strip on the right: E at its first column, my last H
-                    if (has_right && lane == 31) {
-                        const int cout = __viaddmax_s32(cin, 32 * e8, w);
+                    if (has_right) {
+                        const int cout = __viaddmax_s32(cin, 32 * e8, w);  // meaningful in lane 31 (inclusive scan)
                         const uint32_t payload = __byte_perm((uint32_t)cout, H[3], 0x7610);
                         if (right_smem) {
-                            while (cdone < r - PS_D) {
+                            while (cdone < r - PS_D) {  // all lanes track the consumer's progress (broadcast read)
                                 cdone = ps_lds32(done_out);
                                 if (cdone < r - PS_D) __nanosleep(100);
                             }
-                            ps_sts64(mb_out + (uint32_t)(r & (PS_D - 1)) * 8u, ((unsigned long long)(uint32_t)r << 32) | payload);
-                        } else {
-                            passb[r] = payload;
+                            if (lane == 31)
+                                ps_sts64(mb_out + (uint32_t)(r & (PS_D - 1)) * 8u, ((unsigned long long)(uint32_t)r << 32) | payload);
+                        } else if (lane == 31) {
+                            hf[passb_o + (uint32_t)r] = payload;
                         }
                     }
                     // ---- the row enters the ring (entry of row r-PS_K, which no later row reads from the ring) and,
                     // if a row further than PS_K ahead needs it, its spill slot in HBM
                     idx = (idx == K - 1) ? 0 : idx + 1;
-                    ring[idx * 64] = make_uint4(H[0], H[1], H[2], H[3]);
-                    ring[idx * 64 + 32] = make_uint4(Fv[0], Fv[1], Fv[2], Fv[3]);
-                    if (lane0) hring[idx] = msgH;
+                    ps_sts128(ring_s + (uint32_t)idx * 1024u, H[0], H[1], H[2], H[3]);
+                    ps_sts128(ring_s + (uint32_t)idx * 1024u + 512u, Fv[0], Fv[1], Fv[2], Fv[3]);
+                    if (lane0) ps_sts32(hring_s + (uint32_t)idx * 4u, msgH);
                     const uint32_t myslot = cur.x >> 16;
                     if (myslot) {
-                        uint32_t *dst = hfs + (size_t)myslot * hf_stride;
+                        uint32_t *dst = hf + (hfs_o + myslot * hf_stride);
                         *reinterpret_cast<uint4 *>(dst) = make_uint4(H[0], H[1], H[2], H[3]);
                         *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(Fv[0], Fv[1], Fv[2], Fv[3]);
-                        if (lane0) halo_s[(size_t)myslot * nst] = msgH;
+                        if (lane0) hf[halo_so + myslot * (uint32_t)nst] = (uint32_t)msgH;
                     }
 
                     // ---- traceback codes
@@ -395,13 +419,13 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                     if (m > bestv) {
                         bestv = m;
                         bestr = r;
-                        s_bh[tid] = make_uint4(H[0], H[1], H[2], H[3]);
+                        *reinterpret_cast<uint4 *>(mine) = make_uint4(H[0], H[1], H[2], H[3]);
                     }
                     __syncwarp();  // ring entry of row r complete before the next row's reads
                 }
                 // fold this pass' best into the lane's running best: larger H, then smaller row, then smaller column
                 if (bestv > 0) {
-                    const uint4 b4 = s_bh[tid];
+                    const uint4 b4 = *reinterpret_cast<const uint4 *>(mine);
                     const uint32_t bh[4] = {b4.x, b4.y, b4.z, b4.w};
                     int u = 0;
 #pragma unroll
@@ -410,10 +434,11 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                         if (val == bestv) u = x;
                     }
                     const int col = j0 + u + 1;
+                    const int gbv = (int)mine[4], gbr = (int)mine[5], gbc = (int)mine[6];
                     if (bestv > gbv || (bestv == gbv && (bestr < gbr || (bestr == gbr && col < gbc)))) {
-                        gbv = bestv;
-                        gbr = bestr;
-                        gbc = col;
+                        mine[4] = (uint32_t)bestv;
+                        mine[5] = (uint32_t)bestr;
+                        mine[6] = (uint32_t)col;
                     }
                 }
             }
@@ -422,7 +447,7 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
 
         // global maximum: largest H, then first row in rank order, then first column
         // (simd_alignment_engine.cpp:1162-1167,1194-1196); the traceback runs in k_poa_strip_traceback
-        int best = gbv, bi = gbr, bj = gbc;
+        int best = (int)mine[4], bi = (int)mine[5], bj = (int)mine[6];
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             const int ob = __shfl_xor_sync(0xffffffffu, best, d);

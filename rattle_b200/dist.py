@@ -25,13 +25,21 @@ class _DevView:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3}
 
 
-def make_allreduce_callback(group=None):
-    """callback(ptr, count) for Context.set_shard: min-reduces `count` uint32 at device pointer `ptr` over NCCL"""
+def make_allreduce_callback(cuda_stream, group=None):
+    """callback(ptr, count) for Context.set_shard: min-reduces `count` uint32 at device pointer `ptr` over NCCL.
+
+    `cuda_stream` is the raw handle of the stream the Context runs on (the one passed to Context.set_stream; it must
+    not be 0: the legacy default stream does not order against the library's own non-blocking stream).  The
+    reduction is enqueued on that stream, between the kernels that produce and consume the decision arrays."""
     import torch
+    if not cuda_stream:
+        raise ValueError("make_allreduce_callback needs the explicit (non-default) CUDA stream the Context runs on")
+    ext = torch.cuda.ExternalStream(cuda_stream)
 
     def cb(ptr, count):
-        t = torch.as_tensor(_DevView(ptr, count), device="cuda")
-        allreduce_min_u32_(t, group)
+        with torch.cuda.stream(ext):
+            t = torch.as_tensor(_DevView(ptr, count), device="cuda")
+            allreduce_min_u32_(t, group)
         return 0
     return cb
 
