@@ -115,7 +115,8 @@ int rtl_extract_kmers(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, 
                       uint64_t *bv_fwd, uint64_t *bv_rev);
 /* For every (seed s, target t) pair: common[s*n_targets+t] = popcount(bv[seed]&bv[target]) | rev_common<<16,
  * pass[..] bit0 = forward branch taken, bit1 = reverse branch taken at `bv_threshold` (cluster.cpp:19,43).
- * Operates on the reads of the last rtl_reads_upload + an internal extraction with (kmer_size, !is_rna). */
+ * Operates on the reads of the last rtl_reads_upload + an internal extraction with (kmer_size, !is_rna).
+ * common and pass may both be NULL: the scan runs without storing results (kernel timing, rtl_stats.bv_ms). */
 int rtl_bv_scan(rtl_ctx *ctx, int kmer_size, int is_rna, const int32_t *seed_reads, int n_seeds,
                 const int32_t *target_reads, int n_targets, double bv_threshold, uint32_t *common, uint8_t *pass);
 /* For every task (a_read[i], b_read[i], strand[i]): n_common = |get_common_kmers|, bases and n_dist/var from

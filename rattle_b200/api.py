@@ -234,9 +234,13 @@ class Context:
                                              _ptr(fh), _ptr(fp), _ptr(rh), _ptr(rp), _ptr(bf), _ptr(br)))
         return fh, fp, rh, rp, bf, br
 
-    def bv_scan(self, seed_reads, target_reads, bv_threshold, kmer_size=10, is_rna=False):
+    def bv_scan(self, seed_reads, target_reads, bv_threshold, kmer_size=10, is_rna=False, want_output=True):
         s = np.ascontiguousarray(seed_reads, np.int32)
         t = np.ascontiguousarray(target_reads, np.int32)
+        if not want_output:  # kernel timing only (tools/bv_stream_bench.py): results stay on the device
+            self._check(self.L.rtl_bv_scan(self.h, kmer_size, int(is_rna), _ptr(s), len(s), _ptr(t), len(t),
+                                           bv_threshold, None, None))
+            return None
         common = np.zeros((len(s), len(t)), np.uint32)
         passed = np.zeros((len(s), len(t)), np.uint8)
         self._check(self.L.rtl_bv_scan(self.h, kmer_size, int(is_rna), _ptr(s), len(s), _ptr(t), len(t), bv_threshold,

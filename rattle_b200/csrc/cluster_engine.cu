@@ -352,12 +352,13 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, double 
             a.order_check = 1;
             a.rank = ctx->rank;
             a.world = ctx->world;
+            a.ts_cap = BVS_TS;
             a.tasks = S.tasks.p;
             a.n_tasks = S.counters.p;
             a.task_cap = (int64_t)S.tasks.cap;
             a.ovf = S.flags.p + 1;
             a.pair_counter = S.counters.p + 3;
-            dim3 grid((W + 7) / 8, (W + BVS_TS - 1) / BVS_TS);
+            dim3 grid((W + 15) / 16, (W + BVS_TS - 1) / BVS_TS);  // 8 warps x 2 targets per CTA iteration
             S.ev.begin(EV_BV, st);
             k_bv_scan<<<grid, BVS_THREADS, BVS_TS * 64 * 8 + BVS_TS * 8, st>>>(a);
             CK(cudaGetLastError());
@@ -397,13 +398,14 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, double 
             a.order_check = 0;
             a.rank = ctx->rank;
             a.world = ctx->world;
+            a.ts_cap = BVS_TS;
             a.tasks = S.tasks.p;
             a.n_tasks = S.counters.p;
             a.task_cap = (int64_t)S.tasks.cap;
             a.ovf = S.flags.p + 1;
             a.pair_counter = S.counters.p + 3;
             const int64_t nt = c1 - c0;
-            int gx = (int)std::min<int64_t>((nt + 7) / 8, (int64_t)ctx->n_sm * 8);
+            int gx = (int)std::min<int64_t>((nt + 15) / 16, (int64_t)ctx->n_sm * 8);
             dim3 grid(gx, (W + BVS_TS - 1) / BVS_TS);
             S.ev.begin(EV_BV, st);
             k_bv_scan<<<grid, BVS_THREADS, BVS_TS * 64 * 8 + BVS_TS * 8, st>>>(a);
@@ -594,8 +596,8 @@ void cluster_bv_scan_dense(rtl_ctx *ctx, int k, int is_rna, const int32_t *seed_
     CK(cudaMemcpyAsync(d_tg.need(n_targets), target_reads, (size_t)n_targets * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_ns.need(1), &n_seeds, 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_cut.need(4097), cut.data(), 4097 * 2, cudaMemcpyHostToDevice, st));
-    d_common.need(np);
-    d_pass.need(np);
+    if (common) d_common.need(np);
+    if (pass) d_pass.need(np);
     CK(cudaMemsetAsync(d_cnt.need(2), 0, 16, st));
     CK(cudaMemsetAsync(d_ovf.need(1), 0, 4, st));
     BvScanArgs a{};
@@ -614,19 +616,31 @@ void cluster_bv_scan_dense(rtl_ctx *ctx, int k, int is_rna, const int32_t *seed_
     a.order_check = 0;
     a.rank = 0;
     a.world = 1;
+    a.ts_cap = std::max(1, std::min(BVS_TS, n_seeds));
     a.tasks = nullptr;
     a.n_tasks = d_cnt.p;
     a.ovf = d_ovf.p;
-    a.dense_common = d_common.p;
-    a.dense_pass = d_pass.p;
+    a.dense_common = common ? d_common.p : nullptr;  // NULL outputs: scan only (timing runs)
+    a.dense_pass = pass ? d_pass.p : nullptr;
     a.pair_counter = d_cnt.p + 1;
-    int gx = (int)std::min<int64_t>(((int64_t)n_targets + 7) / 8, (int64_t)ctx->n_sm * 8);
-    dim3 grid(std::max(gx, 1), (n_seeds + BVS_TS - 1) / BVS_TS);
-    k_bv_scan<<<grid, BVS_THREADS, BVS_TS * 64 * 8 + BVS_TS * 8, st>>>(a);
+    int gx = (int)std::min<int64_t>(((int64_t)n_targets + 15) / 16, (int64_t)ctx->n_sm * 8);
+    dim3 grid(std::max(gx, 1), (n_seeds + a.ts_cap - 1) / a.ts_cap);
+    S.ev.acc[EV_BV] = 0;
+    S.ev.begin(EV_BV, st);
+    k_bv_scan<<<grid, BVS_THREADS, (size_t)a.ts_cap * (64 * 8 + 8), st>>>(a);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(common, d_common.p, np * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(pass, d_pass.p, np, cudaMemcpyDeviceToHost, st));
+    S.ev.end(EV_BV, st);
+    unsigned long long hcnt[2] = {0, 0};
+    CK(cudaMemcpyAsync(hcnt, d_cnt.p, 16, cudaMemcpyDeviceToHost, st));
+    if (common) CK(cudaMemcpyAsync(common, d_common.p, np * 4, cudaMemcpyDeviceToHost, st));
+    if (pass) CK(cudaMemcpyAsync(pass, d_pass.p, np, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    S.ev.collect();
+    // counters of this launch (tools/bv_stream_bench.py times the scan kernel alone through them)
+    ctx->stats.bv_ms = S.ev.acc[EV_BV];
+    ctx->stats.bv_pairs = (int64_t)hcnt[1];
+    ctx->stats.bv_launches = 1;
+    ctx->stats.kernel_launches = 1;
 }
 
 void cluster_pair_similarity(rtl_ctx *ctx, int k, int is_rna, const int32_t *a_read, const int32_t *b_read,

@@ -237,6 +237,7 @@ struct BvScanArgs {
     int both;                  // reverse strand evaluated
     int order_check;           // require seed item < target item
     int rank, world;           // target sharding
+    int ts_cap;                // seeds per tile the shared memory is sized for (<= BVS_TS; fewer seeds -> more CTAs/SM)
     uint64_t *tasks;
     unsigned long long *n_tasks;
     int64_t task_cap;
@@ -248,13 +249,14 @@ struct BvScanArgs {
 
 __global__ void __launch_bounds__(BVS_THREADS) k_bv_scan(BvScanArgs A) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    uint64_t *sseed = (uint64_t *)sm_raw;                 // [TS][64]
-    int32_t *sitem = (int32_t *)(sseed + BVS_TS * 64);    // [TS]
-    int32_t *spc = sitem + BVS_TS;                        // [TS]
+    const int TS = A.ts_cap;
+    uint64_t *sseed = (uint64_t *)sm_raw;             // [TS][64]
+    int32_t *sitem = (int32_t *)(sseed + TS * 64);    // [TS]
+    int32_t *spc = sitem + TS;                        // [TS]
     const int n_seeds = *A.n_seeds_p;
-    const int s0 = blockIdx.y * BVS_TS;
+    const int s0 = blockIdx.y * TS;
     if (s0 >= n_seeds) return;
-    const int ts = min(BVS_TS, n_seeds - s0);
+    const int ts = min(TS, n_seeds - s0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < ts * 64; i += BVS_THREADS) {
         int s = i >> 6;
@@ -271,29 +273,82 @@ __global__ void __launch_bounds__(BVS_THREADS) k_bv_scan(BvScanArgs A) {
     __syncthreads();
     int n_t = A.tgt_list ? (A.n_tgt_p ? *A.n_tgt_p : A.t1) : (A.t1 - A.t0);
     unsigned long long my_pairs = 0;
-    for (int x = blockIdx.x * (BVS_THREADS / 32) + warp; x < n_t; x += gridDim.x * (BVS_THREADS / 32)) {
-        const int tslot = A.tgt_list ? x : A.t0 + x;  // value stored in the task
-        const int item = A.tgt_list ? A.tgt_list[x] : tslot;
-        if (A.world > 1 && (item % A.world) != A.rank) continue;
-        if (A.taken && A.taken[item]) continue;
-        const uint32_t rd = A.item_read ? (uint32_t)A.item_read[item] : (uint32_t)item;
-        const ulonglong2 f = *reinterpret_cast<const ulonglong2 *>(A.bv_f + (uint64_t)rd * 64 + 2 * lane);
-        ulonglong2 rv = make_ulonglong2(0, 0);
-        if (A.both) rv = *reinterpret_cast<const ulonglong2 *>(A.bv_r + (uint64_t)rd * 64 + 2 * lane);
-        const int pcj = A.pc[rd];
-        for (int g = 0; g < ts; g += 32) {
+    // Half a warp per target (two targets per warp iteration): every lane holds 32 bytes of the target's forward
+    // and reverse bitvector, so one warp instruction scores a seed against two reads and the cross-lane sum is a
+    // 4-step butterfly over 16 lanes.  The loop is software-pipelined two iterations deep: stage A resolves WHICH
+    // read the target two iterations ahead is (target list, taken flag, cluster -> representative read: one
+    // dependent load), stage B requests the bitvectors of the next iteration's target, and the current one is scored.
+    const int half = lane >> 4, sub = lane & 15;
+    const int stride = gridDim.x * (BVS_THREADS / 32) * 2;
+    struct Pre {  // stage A
+        int tslot, item;
+        uint32_t rd;
+        bool live;
+    };
+    struct Tgt {  // stage B
+        ulonglong2 f0, f1, r0, r1;
+        int tslot, item, pcj;
+        bool live;
+    };
+    auto stage_a = [&](int x) -> Pre {
+        Pre p;
+        p.tslot = p.item = 0;
+        p.rd = 0;
+        p.live = false;
+        if (x >= n_t) return p;
+        p.tslot = A.tgt_list ? x : A.t0 + x;  // value stored in the task
+        p.item = A.tgt_list ? A.tgt_list[x] : p.tslot;
+        if (A.world > 1 && (p.item % A.world) != A.rank) return p;
+        const bool taken = A.taken ? (A.taken[p.item] != 0) : false;
+        p.rd = A.item_read ? (uint32_t)A.item_read[p.item] : (uint32_t)p.item;
+        p.live = !taken;
+        return p;
+    };
+    auto stage_b = [&](const Pre &p) -> Tgt {
+        Tgt t;
+        t.f0 = t.f1 = t.r0 = t.r1 = make_ulonglong2(0, 0);
+        t.tslot = p.tslot;
+        t.item = p.item;
+        t.pcj = 0;
+        t.live = p.live;
+        if (!p.live) return t;
+        const ulonglong2 *pf = reinterpret_cast<const ulonglong2 *>(A.bv_f + (uint64_t)p.rd * 64 + 4 * sub);
+        t.f0 = pf[0];
+        t.f1 = pf[1];
+        if (A.both) {
+            const ulonglong2 *pr = reinterpret_cast<const ulonglong2 *>(A.bv_r + (uint64_t)p.rd * 64 + 4 * sub);
+            t.r0 = pr[0];
+            t.r1 = pr[1];
+        }
+        t.pcj = A.pc[p.rd];
+        return t;
+    };
+    int x = (blockIdx.x * (BVS_THREADS / 32) + warp) * 2 + half;  // my half-warp's target
+    Tgt nxt = stage_b(stage_a(x));
+    Pre pre = stage_a(x + stride);
+    for (int xw = x - half; xw < n_t; xw += stride, x += stride) {  // xw: warp-uniform loop variable
+        const Tgt cur = nxt;
+        nxt = stage_b(pre);
+        pre = stage_a(x + 2 * stride);
+        if (!__any_sync(0xffffffffu, cur.live)) continue;
+        const int tslot = cur.tslot, item = cur.item, pcj = cur.pcj;
+        for (int g = 0; g < ts; g += 16) {
             uint32_t mine = 0;
-            const int lim = min(32, ts - g);
+            const int lim = min(16, ts - g);
             for (int q = 0; q < lim; ++q) {
-                const ulonglong2 sw = *reinterpret_cast<const ulonglong2 *>(sseed + (g + q) * 64 + 2 * lane);
-                uint32_t c = (uint32_t)(__popcll(sw.x & f.x) + __popcll(sw.y & f.y));
-                c |= (uint32_t)(__popcll(sw.x & rv.x) + __popcll(sw.y & rv.y)) << 16;
+                const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(sseed + (g + q) * 64 + 4 * sub);
+                const ulonglong2 s0v = sp[0], s1v = sp[1];
+                uint32_t c = (uint32_t)(__popcll(s0v.x & cur.f0.x) + __popcll(s0v.y & cur.f0.y) + __popcll(s1v.x & cur.f1.x) +
+                                        __popcll(s1v.y & cur.f1.y));
+                c |= (uint32_t)(__popcll(s0v.x & cur.r0.x) + __popcll(s0v.y & cur.r0.y) + __popcll(s1v.x & cur.r1.x) +
+                                __popcll(s1v.y & cur.r1.y))
+                     << 16;
 #pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1) c += __shfl_xor_sync(0xffffffffu, c, sft);
-                if (lane == q) mine = c;
+                for (int sft = 8; sft > 0; sft >>= 1) c += __shfl_xor_sync(0xffffffffu, c, sft);
+                if (sub == q) mine = c;
             }
-            const int s = g + lane;
-            bool valid = lane < lim;
+            const int s = g + sub;
+            bool valid = cur.live && sub < lim;
             if (valid && A.order_check) valid = sitem[s] < item;
             const uint32_t cf = mine & 0xffffu, cr = mine >> 16;
             bool pf = false, pr = false;
@@ -305,7 +360,7 @@ __global__ void __launch_bounds__(BVS_THREADS) k_bv_scan(BvScanArgs A) {
             }
             my_pairs += (unsigned long long)__popc(__ballot_sync(0xffffffffu, valid));
             if (A.dense_common) {
-                if (lane < lim) {
+                if (cur.live && sub < lim) {
                     size_t idx = (size_t)(s0 + s) * (size_t)n_t + (size_t)x;
                     A.dense_common[idx] = mine;
                     A.dense_pass[idx] = (uint8_t)((pf ? 1 : 0) | (pr ? 2 : 0));

@@ -130,3 +130,60 @@ def test_correct_golden(ctx):
     assert hashlib.sha256(out[1]).hexdigest() == g["uncorrected_sha256"]
     assert hashlib.sha256(out[0]).hexdigest() == g["corrected_sha256"]
     assert out[2].decode().splitlines()[:2] == g["consensi_head"]
+
+
+# ---- int16 strip kernel (poa_strip_kernel.cuh): geometry and graph-shape edge cases, all against the reference
+@pytest.mark.parametrize("length,n", [(5, 4), (9, 5), (255, 5), (256, 5), (257, 6), (2049, 5), (3500, 4)])
+def test_poa_strip_boundaries(ctx, ref, length, n):
+    """query lengths around the lane (8), strip (256) and pass (8 strips) boundaries; 3500 = two passes of 7 strips"""
+    rs = pack(11 + length % 7, n, float(length), trunc_max=0)
+    rows, alns = ctx.poa_msa(rs.bases, rs.offsets, want_alignments=True)
+    erows, ealns = ref.poa_msa(rs.bases, rs.offsets, want_alignments=True)
+    for i, (a, b) in enumerate(zip(alns, ealns)):
+        assert np.array_equal(a, b), "alignment %d differs" % i
+    assert rows == erows
+
+
+def test_poa_strip_bushy_graph_spilled_rows(ctx, ref):
+    """60 noisy reads: rows with more than 3 predecessors (overflow list) and predecessors further back than the
+    shared-memory ring (spilled rows read back from HBM)"""
+    rs = pack(21, 60, 700.0, p_sub=0.06, p_ins=0.04, p_del=0.04)
+    rows, alns = ctx.poa_msa(rs.bases, rs.offsets, want_alignments=True)
+    erows, ealns = ref.poa_msa(rs.bases, rs.offsets, want_alignments=True)
+    for i, (a, b) in enumerate(zip(alns, ealns)):
+        assert np.array_equal(a, b), "alignment %d differs" % i
+    assert rows == erows
+
+
+def test_poa_strip_mixed_lengths_and_letters(ctx, ref):
+    """reads of very different lengths in one pack (several CTA widths over the steps), U instead of T, an unrelated
+    read (no positive score -> empty alignment) and a read with N (not representable -> int32 kernel)"""
+    rs = pack(31, 10, 900.0)
+    seqs = [rs.seq(i) for i in range(rs.n)]
+    seqs[3] = seqs[3][:300]
+    seqs[4] = seqs[4][200:260]
+    seqs[5] = seqs[5].replace(b"T", b"U")
+    seqs.insert(6, b"G" * 40)
+    rs2 = synth.from_sequences(seqs)
+    rows, alns = ctx.poa_msa(rs2.bases, rs2.offsets, want_alignments=True)
+    erows, ealns = ref.poa_msa(rs2.bases, rs2.offsets, want_alignments=True)
+    for i, (a, b) in enumerate(zip(alns, ealns)):
+        assert np.array_equal(a, b), "alignment %d differs" % i
+    assert rows == erows
+    seqs[2] = seqs[2][:100] + b"N" + seqs[2][101:]
+    rs3 = synth.from_sequences(seqs)
+    assert ctx.poa_msa(rs3.bases, rs3.offsets) == ref.poa_msa(rs3.bases, rs3.offsets)
+
+
+def test_poa_int32_kernel_still_matches(ctx, ref):
+    """option poa_kernel=1 forces the first-generation int32 kernel (the fallback for other scores / letters)"""
+    rs = pack(5, 10, 600.0)
+    ctx.set_option("poa_kernel", 1)
+    try:
+        rows, alns = ctx.poa_msa(rs.bases, rs.offsets, want_alignments=True)
+    finally:
+        ctx.set_option("poa_kernel", 0)
+    erows, ealns = ref.poa_msa(rs.bases, rs.offsets, want_alignments=True)
+    for a, b in zip(alns, ealns):
+        assert np.array_equal(a, b)
+    assert rows == erows
