@@ -144,6 +144,11 @@ int rtl_correct_reads(rtl_ctx *ctx, const char *bases, const char *quals, const 
                       int64_t *corrected_len, char *uncorrected, int64_t *uncorrected_len, char *consensi,
                       int64_t *consensi_len);
 
+/* File labels of `rattle correct -l a,b,...` (main.cpp:383): the consensus headers then carry per-label read counts
+ * ("labels=a:12,b:3,", correct.cpp:447-470,488-512).  Applies to the following rtl_correct_reads calls on this ctx;
+ * n_labels = 0 (the default) gives the reference's label-less headers ("labels="). */
+int rtl_set_labels(rtl_ctx *ctx, const char *const *labels, int n_labels);
+
 /* -------------------------------------------------------------------------------- clusters.out codec */
 int64_t rtl_hps_encode(int n_clusters, const int32_t *main_id, const uint8_t *main_rev, const int32_t *main_gene,
                        const int64_t *cl_off, const int32_t *mem_id, const uint8_t *mem_rev,

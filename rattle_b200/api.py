@@ -38,7 +38,7 @@ ALLREDUCE_FN = ctypes.CFUNCTYPE(c_i, c_p, c_p, c_i64)
 # every symbol include/rattle_b200.h declares (tests/test_boundary.py checks the header against this list)
 SYMBOLS = ["rtl_init", "rtl_destroy", "rtl_last_error", "rtl_set_option", "rtl_set_stream", "rtl_get_stats", "rtl_cluster_reads",
            "rtl_reads_upload", "rtl_cluster_resident", "rtl_set_shard", "rtl_extract_kmers", "rtl_bv_scan",
-           "rtl_pair_similarity", "rtl_poa_msa", "rtl_correct_reads", "rtl_hps_encode", "rtl_hps_decode"]
+           "rtl_pair_similarity", "rtl_poa_msa", "rtl_correct_reads", "rtl_set_labels", "rtl_hps_encode", "rtl_hps_decode"]
 
 _lib = None
 
@@ -79,6 +79,8 @@ def load_library():
     L.rtl_set_shard.argtypes = [c_p, c_i, c_i, ALLREDUCE_FN, c_p]
     L.rtl_extract_kmers.restype = c_i
     L.rtl_extract_kmers.argtypes = [c_p, c_p, c_p, c_u32, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]
+    L.rtl_set_labels.restype = c_i
+    L.rtl_set_labels.argtypes = [c_p, c_p, c_i]
     L.rtl_bv_scan.restype = c_i
     L.rtl_bv_scan.argtypes = [c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_d, c_p, c_p]
     L.rtl_pair_similarity.restype = c_i
@@ -160,6 +162,11 @@ class Context:
     def set_stream(self, cuda_stream: int):
         """cuda_stream: a cudaStream_t as int (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream."""
         self._check(self.L.rtl_set_stream(self.h, c_p(cuda_stream) if cuda_stream else None))
+
+    def set_labels(self, labels):
+        """file labels of `rattle correct -l` (consensus headers then carry per-label read counts)"""
+        arr = (ctypes.c_char_p * max(1, len(labels)))(*[x.encode() if isinstance(x, str) else x for x in labels])
+        self._check(self.L.rtl_set_labels(self.h, arr, len(labels)))
 
     def stats(self) -> dict:
         s = Stats()

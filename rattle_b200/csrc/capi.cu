@@ -129,6 +129,13 @@ int rtl_set_option(rtl_ctx *ctx, const char *key, int64_t value) {
     return RTL_OK;
 }
 
+int rtl_set_labels(rtl_ctx *ctx, const char *const *labels, int n_labels) {
+    if (!ctx || n_labels < 0 || (n_labels > 0 && !labels)) return RTL_ERR_STATE;
+    ctx->labels.clear();
+    for (int i = 0; i < n_labels; ++i) ctx->labels.emplace_back(labels[i] ? labels[i] : "");
+    return RTL_OK;
+}
+
 int rtl_set_stream(rtl_ctx *ctx, void *cuda_stream) {
     if (!ctx) return RTL_ERR_STATE;
     cudaSetDevice(ctx->device);

@@ -469,15 +469,25 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
         }
     }
     lap("output assembly");
-    // ---- pack consensus headers (correct.cpp:447-470; no file labels through this entry point)
+    // ---- pack consensus headers (correct.cpp:447-470), literally, file labels included (rtl_set_labels)
+    const std::vector<std::string> &labels = ctx->labels;
     std::vector<std::vector<Read>> consensi(n_clusters);
     for (auto &p : packs) {
         std::string gid;
+        std::vector<std::string> labelset;
         for (const auto &r : p.creads) {
+            if (!labels.empty()) {
+                int index = (int)r.header.find_first_of(",");
+                int i = (int)r.header.substr(index + 1).find_first_of(",");
+                labelset.push_back(r.header.substr(index + 1, i));
+            }
             const size_t index = r.header.find("gene_cluster");
             gid = std::to_string(std::stoi(r.header.substr(index + 13)));
         }
-        consensi[p.cid].push_back(Read{gid + "," + std::to_string(p.creads.size()) + ",", p.consensus, "+",
+        std::string label_result;
+        for (const auto &label : labels)
+            label_result = label_result + " " + label + ":" + std::to_string(std::count(labelset.begin(), labelset.end(), label));
+        consensi[p.cid].push_back(Read{gid + "," + std::to_string(p.creads.size()) + "," + label_result, p.consensus, "+",
                                        std::string(p.consensus.size(), 'K')});
     }
 
@@ -494,15 +504,33 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
     for (int cid = 0; cid < n_clusters; ++cid) {
         auto &it = consensi[cid];
         int total_reads = 0, gid = 0;
+        std::vector<int> label_counts(labels.size());
         for (const auto &r : it) {
             auto num = split_string(r.header, ',');
             gid = std::stoi(num[0]);
             total_reads += std::stoi(num[1]);
+            int i = 0;
+            for (const auto &label : labels) {  // correct.cpp:498-509
+                if (r.header.find(label) != std::string::npos) {
+                    int index = (int)r.header.find(label);
+                    const std::string sub = r.header.substr(index + 1);
+                    index = (int)sub.find_first_of(":");
+                    try {
+                        label_counts[i] += std::stoi(sub.substr(index + 1));
+                    } catch (const std::exception &) {
+                        throw InputError("file label that cannot be counted in a consensus header (correct.cpp:506)");
+                    }
+                }
+                ++i;
+            }
         }
-        const std::string head = gene_mode
-                                     ? "@gene_cluster_" + std::to_string(cid) + " reads=" + std::to_string(total_reads) + " labels="
-                                     : "@transcript_cluster_" + std::to_string(cid) + " gene_cluster_" + std::to_string(gid) +
-                                           " reads=" + std::to_string(total_reads) + " labels=";
+        std::string labels_result;
+        for (size_t i = 0; i < labels.size(); ++i) labels_result += labels[i] + ":" + std::to_string(label_counts[i]) + ",";
+        const std::string head =
+            (gene_mode ? "@gene_cluster_" + std::to_string(cid) + " reads=" + std::to_string(total_reads) + " labels="
+                       : "@transcript_cluster_" + std::to_string(cid) + " gene_cluster_" + std::to_string(gid) + " reads=" +
+                             std::to_string(total_reads) + " labels=") +
+            labels_result;
         if (it.size() > 1) {
             std::vector<std::string> msa;
             t3[cid].g.msa(msa);
