@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -165,19 +166,20 @@ correction_results_t correct_reads(const cluster_set_t &clusters, read_set_t &re
     std::vector<const char *> lab;
     for (const auto &l : labels) lab.push_back(l.c_str());
     check(rtl_set_labels(context(), lab.data(), (int)lab.size()), "rtl_set_labels");
-    std::string out[3];
-    int64_t len[3] = {0, 0, 0};
-    for (int attempt = 0; attempt < 2; ++attempt) {  // first call reports the sizes (RTL_ERR_CAPACITY)
-        for (int i = 0; i < 3; ++i) out[i].resize((size_t)len[i]);
+    // generous first guess (corrected reads are about as long as the raw ones), exact sizes on RTL_ERR_CAPACITY
+    std::unique_ptr<char[]> out[3];  // uninitialised: untouched pages cost nothing
+    const int64_t guess = 3 * (int64_t)f.bases.size() + (int64_t)f.headers.size() + 64 * (int64_t)(reads.size() + nc) + 1024;
+    int64_t len[3] = {guess, guess, guess};
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        for (int i = 0; i < 3; ++i) out[i].reset(new char[(size_t)len[i] + 1]);
         const int rc = rtl_correct_reads(context(), f.bases.data(), f.quals.data(), f.off.data(), (uint32_t)reads.size(),
                                          f.headers.data(), f.hoff.data(), main_id.data(), main_rev.data(), main_gene.data(),
                                          cl_off.data(), mem_id.data(), mem_rev.data(), mem_gene.data(), nc, min_occ, gap_occ,
-                                         err_ratio, split, min_reads, &out[0][0], &len[0], &out[1][0], &len[1], &out[2][0],
-                                         &len[2]);
+                                         err_ratio, split, min_reads, out[0].get(), &len[0], out[1].get(), &len[1],
+                                         out[2].get(), &len[2]);
         if (rc == RTL_OK) break;
         if (rc != RTL_ERR_CAPACITY || attempt == 1) check(rc, "rtl_correct_reads");
     }
-    for (int i = 0; i < 3; ++i) out[i].resize((size_t)len[i]);
     // the reference edits the caller's reads in place (correct.cpp:338-350): reverse members are reverse-complemented,
     // every member's header gets the cluster suffix; polish reads those headers afterwards (main.cpp:685)
     for (int cid = 0; cid < nc; ++cid) {
@@ -195,5 +197,7 @@ correction_results_t correct_reads(const cluster_set_t &clusters, read_set_t &re
                 else r.header = r.header + ",gene_cluster_" + std::to_string(gid) + ",transcript_cluster_" + std::to_string(cid);
             }
     }
-    return correction_results_t{parse_fastq(out[0]), parse_fastq(out[1]), parse_fastq(out[2])};
+    return correction_results_t{parse_fastq(std::string(out[0].get(), (size_t)len[0])),
+                                parse_fastq(std::string(out[1].get(), (size_t)len[1])),
+                                parse_fastq(std::string(out[2].get(), (size_t)len[2]))};
 }

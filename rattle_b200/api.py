@@ -302,7 +302,7 @@ class Context:
             hdr = np.frombuffer(b"".join(headers), dtype=np.uint8).copy()
         cap = 4 * int(offsets[-1]) + 256 * (n + nc) + 1024
         while True:
-            bufs = [np.zeros(cap, np.uint8) for _ in range(3)]
+            bufs = [np.empty(cap, np.uint8) for _ in range(3)]  # untouched pages cost nothing
             lens = [c_i64(cap) for _ in range(3)]
             args = [self.h, _ptr(bases), _ptr(quals), _ptr(offsets), n, _ptr(hdr), _ptr(hoff), _ptr(clusters.main_id),
                     _ptr(clusters.main_rev), _ptr(gm), _ptr(clusters.cl_off), _ptr(clusters.mem_id),

@@ -386,7 +386,7 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
         }
     }
     // packs that are too small are not corrected (correct.cpp:360-366); their reads go to `uncorrected` first
-    std::string out_c, out_u, out_s;
+    std::string out_u, out_s;
     {
         std::vector<Pack> keep;
         keep.reserve(packs.size());
@@ -452,22 +452,8 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
         poa_account_busy(ctx);
     }
     lap("POA rounds 1+2 with correction");
-    // queue order = the reference's -t 1 order (correct.cpp:413-424)
-    {
-        size_t nc = 0, nu = out_u.size();
-        for (auto &p : packs) {
-            nc += p.fq_corrected.size();
-            nu += p.fq_uncorrected.size();
-        }
-        out_c.reserve(nc);
-        out_u.reserve(nu);
-        for (auto &p : packs) {
-            out_c += p.fq_corrected;
-            out_u += p.fq_uncorrected;
-            std::string().swap(p.fq_corrected);
-            std::string().swap(p.fq_uncorrected);
-        }
-    }
+    // queue order = the reference's -t 1 order (correct.cpp:413-424); the per-pack FASTQ texts are copied into the
+    // caller's buffers at the end, in parallel
     lap("output assembly");
     // ---- pack consensus headers (correct.cpp:447-470), literally, file labels included (rtl_set_labels)
     const std::vector<std::string> &labels = ctx->labels;
@@ -547,21 +533,29 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
     lap("third POA + headers");
     append_fastq(out_s, consensus_set);
     int rc = RTL_OK;
-    auto put = [&](const std::string &s, char *buf, int64_t *len) {
-        if ((int64_t)s.size() > *len || !buf) {
-            *len = (int64_t)s.size();
-            rc = RTL_ERR_CAPACITY;
-            return;
-        }
-        memcpy(buf, s.data(), s.size());
-        *len = (int64_t)s.size();
-    };
-    put(out_c, corrected_out, corrected_len);
-    put(out_u, uncorrected_out, uncorrected_len);
-    put(out_s, consensi_out, consensi_len);
+    // corrected = packs in order; uncorrected = reads of the too-small packs (out_u), then the packs in order
+    std::vector<size_t> off_c(packs.size() + 1, 0), off_u(packs.size() + 1, out_u.size());
+    for (size_t i = 0; i < packs.size(); ++i) {
+        off_c[i + 1] = off_c[i] + packs[i].fq_corrected.size();
+        off_u[i + 1] = off_u[i] + packs[i].fq_uncorrected.size();
+    }
+    const size_t need[3] = {off_c[packs.size()], off_u[packs.size()], out_s.size()};
+    char *const bufs[3] = {corrected_out, uncorrected_out, consensi_out};
+    int64_t *const lens[3] = {corrected_len, uncorrected_len, consensi_len};
+    for (int i = 0; i < 3; ++i)
+        if ((int64_t)need[i] > *lens[i] || !bufs[i]) rc = RTL_ERR_CAPACITY;
+    if (rc == RTL_OK) {
+        memcpy(uncorrected_out, out_u.data(), out_u.size());
+        memcpy(consensi_out, out_s.data(), out_s.size());
+        parallel_for(nthreads, packs.size(), [&](size_t i) {
+            memcpy(corrected_out + off_c[i], packs[i].fq_corrected.data(), packs[i].fq_corrected.size());
+            memcpy(uncorrected_out + off_u[i], packs[i].fq_uncorrected.data(), packs[i].fq_uncorrected.size());
+        });
+    }
+    for (int i = 0; i < 3; ++i) *lens[i] = (int64_t)need[i];
     lap("output");
     ctx->stats.total_ms = now_ms() - t0;
-    ctx->stats.d2h_bytes += (int64_t)(out_c.size() + out_u.size() + out_s.size());
+    ctx->stats.d2h_bytes += (int64_t)(need[0] + need[1] + need[2]);
     if (rc == RTL_ERR_CAPACITY) ctx->err = "output buffer too small (needed sizes returned in *_len)";
     return rc;
 }

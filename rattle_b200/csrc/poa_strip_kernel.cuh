@@ -33,6 +33,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace rtl {
 
 struct PoaSJob {
@@ -92,23 +94,26 @@ __device__ __forceinline__ void ps_sts32(uint32_t addr, int v) {
     asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// H (4 words), F (4 words, 512 B further) and the halo word of one predecessor row: from the shared-memory ring
-// (32-bit shared addresses) or, for a spilled row, from HBM — predicated loads into the same registers, no branch.
-__device__ __forceinline__ void ps_fetch_row(bool far, uint32_t s_row, uint32_t s_halo, const uint32_t *g_row,
-                                             const int *g_halo, uint32_t (&cH)[4], uint32_t (&cF)[4], int &hl) {
+// H (4 words), F (4 words, 512 B further) and the halo word of one predecessor row from the shared-memory ring ...
+__device__ __forceinline__ void ps_fetch_ring(uint32_t s_row, uint32_t s_halo, uint32_t (&cH)[4], uint32_t (&cF)[4], int &hl) {
     asm volatile(
-        "{\n\t"
-        ".reg .pred pf;\n\t"
-        "setp.ne.u32 pf, %9, 0;\n\t"
-        "@pf ld.global.v4.u32 {%0,%1,%2,%3}, [%12];\n\t"
-        "@pf ld.global.v4.u32 {%4,%5,%6,%7}, [%12+512];\n\t"
-        "@pf ld.global.s32 %8, [%13];\n\t"
-        "@!pf ld.shared.v4.u32 {%0,%1,%2,%3}, [%10];\n\t"
-        "@!pf ld.shared.v4.u32 {%4,%5,%6,%7}, [%10+512];\n\t"
-        "@!pf ld.shared.s32 %8, [%11];\n\t"
-        "}"
+        "ld.shared.v4.u32 {%0,%1,%2,%3}, [%9];\n\t"
+        "ld.shared.v4.u32 {%4,%5,%6,%7}, [%9+512];\n\t"
+        "ld.shared.s32 %8, [%10];"
         : "=r"(cH[0]), "=r"(cH[1]), "=r"(cH[2]), "=r"(cH[3]), "=r"(cF[0]), "=r"(cF[1]), "=r"(cF[2]), "=r"(cF[3]), "=r"(hl)
-        : "r"((uint32_t)far), "r"(s_row), "r"(s_halo), "l"(g_row), "l"(g_halo)
+        : "r"(s_row), "r"(s_halo)
+        : "memory");
+}
+// ... overwritten in place, for a spilled row, from HBM ("+r": the same registers, so the rare branch around this
+// block needs no register moves at its join)
+__device__ __forceinline__ void ps_fetch_spilled(const uint32_t *g_row, const uint32_t *g_halo, uint32_t (&cH)[4],
+                                                 uint32_t (&cF)[4], int &hl) {
+    asm volatile(
+        "ld.global.v4.u32 {%0,%1,%2,%3}, [%9];\n\t"
+        "ld.global.v4.u32 {%4,%5,%6,%7}, [%9+512];\n\t"
+        "ld.global.s32 %8, [%10];"
+        : "+r"(cH[0]), "+r"(cH[1]), "+r"(cH[2]), "+r"(cH[3]), "+r"(cF[0]), "+r"(cF[1]), "+r"(cF[2]), "+r"(cF[3]), "+r"(hl)
+        : "l"(g_row), "l"(g_halo)
         : "memory");
 }
 __device__ __forceinline__ void ps_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -286,27 +291,28 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
 #pragma unroll
                     for (int k = 0; k < 4; ++k) dpk[k] = 0u;
                     // ---- predecessors in in_edges order: ring (near) or HBM (spilled rows), predicated loads
-                    auto fetch = [&](uint32_t pw, uint32_t(&cH)[4], uint32_t(&cF)[4], int &hl) {
+                    auto fold = [&](uint32_t pw, int p, auto first) {
+                        uint32_t cH[4], cF[4];
+                        int hl;
                         const bool far = (pw & PS_FAR) != 0u;
-                        const uint32_t slot = pw & 0xffffu;
                         int pi = idx + 1 - (int)(pw & 0xffu);  // ring entry of row r - pw
                         pi += (pi < 0) ? K : 0;
-                        ps_fetch_row(far, ring_s + (uint32_t)pi * 1024u, hring_s + (uint32_t)pi * 4u,
-                                     hf + (hfs_o + slot * hf_stride), reinterpret_cast<const int *>(hf + (halo_so + slot * (uint32_t)nst)), cH, cF, hl);
+                        pi = far ? 0 : pi;  // (a valid entry; its values are replaced below)
+                        ps_fetch_ring(ring_s + (uint32_t)pi * 1024u, hring_s + (uint32_t)pi * 4u, cH, cF, hl);
+                        if (far) {
+                            const uint32_t slot = pw & 0xffffu;
+                            ps_fetch_spilled(hf + (hfs_o + slot * hf_stride), hf + (halo_so + slot * (uint32_t)nst), cH, cF, hl);
+                        }
+                        ps_fold_pred<SG, SE, decltype(first)::value>(cH, cF, hl, lane0, p, sc, Hd, Fv, fpk, dpk);
                     };
-                    {
-                        uint32_t cH[4], cF[4];
-                        int hl;
-                        fetch(cur.y, cH, cF, hl);
-                        ps_fold_pred<SG, SE, true>(cH, cF, hl, lane0, 0, sc, Hd, Fv, fpk, dpk);
-                    }
+                    fold(cur.y, 0, std::true_type());
+                    if (np > 1) {  // straight-line code for the common in-degrees, a loop beyond
+                        fold(cur.z, 1, std::false_type());
+                        if (np > 2) {
+                            fold((np <= 3) ? cur.w : (uint32_t)preds[pred_base + cur.w + 2], 2, std::false_type());
 #pragma unroll 1
-                    for (int p = 1; p < np; ++p) {
-                        const uint32_t pw = (p == 1) ? cur.z : ((np <= 3) ? cur.w : (uint32_t)preds[pred_base + cur.w + p]);
-                        uint32_t cH[4], cF[4];
-                        int hl;
-                        fetch(pw, cH, cF, hl);
-                        ps_fold_pred<SG, SE, false>(cH, cF, hl, lane0, p, sc, Hd, Fv, fpk, dpk);
+                            for (int p = 3; p < np; ++p) fold((uint32_t)preds[pred_base + cur.w + p], p, std::false_type());
+                        }
                     }
 
                     // ---- E: contribution of my own columns, warp scan, carry from the strip on the left
