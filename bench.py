@@ -317,6 +317,8 @@ def main():
         "roofline": roof,
         "kernels_ms_per_step": kern,
         "bv_scan": {"pairs": st["bv_pairs"], "ms": st["bv_ms"], "alg_gbs": bv_gbs, "alg_frac_of_hbm": bv_gbs / hbm},
+        "library_ms": {"cluster_reads": st["total_ms"], "correct_reads": st2["total_ms"] if st2 else 0.0,
+                       "poa_wall": st2["poa_wall_ms"] if st2 else 0.0},
         "counters": {"clusters": int(cl.n_clusters), "waves": st["waves"], "rounds": st["rounds"],
                      "full_pairs": st["full_pairs"], "heavy_pairs": st["heavy_pairs"],
                      "poa_cells": st2["poa_cells"] if st2 else 0, "poa_alignments": st2["poa_alignments"] if st2 else 0},

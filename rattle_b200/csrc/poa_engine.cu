@@ -198,9 +198,19 @@ void parallel_for(int n_threads, size_t n, const std::function<void(size_t)> &fn
     if (job.err) std::rethrow_exception(job.err);
 }
 
+// Host threads of this process: all cores, or this rank's share of them when several ranks run on one node
+// (torchrun exports LOCAL_WORLD_SIZE; RATTLE_B200_THREADS overrides) — oversubscribed cores only add contention.
 int host_threads() {
+    if (const char *e = getenv("RATTLE_B200_THREADS")) {
+        const int v = atoi(e);
+        if (v > 0) return std::min(v, 256);
+    }
     unsigned hc = std::thread::hardware_concurrency();
     if (hc == 0) hc = 4;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) {
+        const int w = atoi(e);
+        if (w > 1) hc = std::max(4u, hc / (unsigned)w);
+    }
     return (int)std::min(hc, 64u);
 }
 
