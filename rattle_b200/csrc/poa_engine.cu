@@ -18,6 +18,7 @@
 #include "poa_engine.hpp"
 #include "poa_kernels.cuh"
 #include "poa_strip_kernel.cuh"
+#include "poa_devgraph.cuh"
 
 using namespace rtl;
 
@@ -32,6 +33,10 @@ struct JobRef {
     int n_spill = 0;             // JK_STRIP: rows that are also written to HBM (needed more than PS_K rows later)
     size_t hf_bytes, code_bytes; // device arena need
     int L, n;
+    // graphs with a device mirror (poa_devgraph.cuh): row records / predecessor words / spill rows are produced on the
+    // device by k_poa_graph_fold at these (absolute) offsets of the slot's d_rec / d_preds / d_spill
+    bool mirror = false;
+    uint32_t rec_off = 0, pred_base = 0, spill_off = 0;
 };
 
 // One unit's slot: its own staging buffers, stream and slice of the device arena.
@@ -46,6 +51,12 @@ struct PoaSlot {
     DevBuf<int4> d_best;
     DevBuf<int32_t> d_spill;
     PinBuf<int32_t> h_spill;
+    // device mirrors of this unit's graphs and the per-step fold staging
+    DevBuf<int32_t> d_pool, d_delta, d_counts;
+    PinBuf<int32_t> h_delta, h_counts;
+    DevBuf<DFoldJob> d_fjobs;
+    PinBuf<DFoldJob> h_fjobs;
+    size_t base_rows = 0, base_preds = 0, base_spill = 0;  // first host-staged entry of d_rec / d_preds / d_spill this step
     PinBuf<uint8_t> h_q;
     PinBuf<uint32_t> h_row_info, h_row_poff;
     PinBuf<int32_t> h_preds, h_aln, h_aln_len;
@@ -325,6 +336,19 @@ static int plan_spills(PoaTask *t, int K) {
     return ns;
 }
 
+// strip kernel, graphs with a device mirror: only the query is staged by the host
+static void stage_strip_query(const JobRef &jr, PoaSJob &J, uint8_t *q) {
+    const uint8_t *tab = letter_codes();
+    const char *src = jr.task->seq[jr.seq_index];
+    for (int i = 0; i < jr.L; ++i) q[i] = tab[(unsigned char)src[i]];
+    memset(q + jr.L, 255, (size_t)jr.nst * PS_STRIP - jr.L);
+    J.L = jr.L;
+    J.n = jr.n;
+    J.n_strips = jr.nst;
+    J.n_spill = jr.n_spill;
+    J.pad = 0;
+}
+
 // strip kernel, step 2: letter codes of the query (padded with 255 to whole strips), one 16-byte record per row
 // (layout: poa_strip_kernel.cuh), the predecessor words of rows with more than 3 predecessors, and the row of
 // every spill slot (for the traceback)
@@ -409,16 +433,18 @@ static void submit(rtl_ctx *ctx, PoaState &P, PoaSlot &S, std::vector<JobRef> &&
         const JobRef &jr = jobs[i];
         const bool strip = jr.kind == JK_STRIP;
         q_off[i + 1] = q_off[i] + (strip ? (size_t)jr.nst * PS_STRIP : (size_t)((poa_lp(jr.L) + 4 + 15) & ~15));
-        row_off[i] = strip ? rows_strip : rows_old;
-        (strip ? rows_strip : rows_old) += (size_t)jr.n + 1;
-        pred_off[i] = preds_total;
-        preds_total += jr.task->g.e_begin.size() + (size_t)jr.n;  // upper bound (sources count 1 each)
+        if (!jr.mirror) {  // host-staged graph description
+            row_off[i] = strip ? rows_strip : rows_old;
+            (strip ? rows_strip : rows_old) += (size_t)jr.n + 1;
+            pred_off[i] = preds_total;
+            preds_total += jr.task->g.e_begin.size() + (size_t)jr.n;  // upper bound (sources count 1 each)
+        }
         S.aln_off[i + 1] = S.aln_off[i] + jr.n + jr.L + 8;
         hf_off[i] = arena_at;
         arena_at += (jr.hf_bytes + 255) & ~(size_t)255;
         code_off[i] = arena_at;
         arena_at += (jr.code_bytes + 255) & ~(size_t)255;
-        spill_off[i + 1] = spill_off[i] + (strip ? (size_t)jr.n_spill + 1 : 0);
+        spill_off[i + 1] = spill_off[i] + ((strip && !jr.mirror) ? (size_t)jr.n_spill + 1 : 0);
     }
     if (arena_at > S.arena_bytes) throw StateError("POA group exceeds the unit's arena");
     if (q_off[nj] >= (1ull << 32) || rows_old >= (1ull << 32) || rows_strip >= (1ull << 32) ||
@@ -440,18 +466,27 @@ static void submit(rtl_ctx *ctx, PoaState &P, PoaSlot &S, std::vector<JobRef> &&
             J.hf_off = hf_off[i] / 4;
             J.code_off = code_off[i] / 4;
             J.q_off = (uint32_t)q_off[i];
-            J.row_off = (uint32_t)row_off[i];
-            J.pred_base = (uint32_t)pred_off[i];
             J.aln_off = (uint32_t)aln_off[i];
-            J.spill_off = (uint32_t)spill_off[i];
-            stage_strip_job(jr, J, hq + q_off[i], hrec + row_off[i], hpr + pred_off[i], hsp + spill_off[i]);
+            if (jr.mirror) {  // records are already on the device (k_poa_graph_fold); only the query is staged
+                J.row_off = jr.rec_off;
+                J.pred_base = jr.pred_base;
+                J.spill_off = jr.spill_off;
+                J.order_off = jr.task->gbase + 4 * (uint64_t)jr.task->cap_n;  // DGView::order
+                stage_strip_query(jr, J, hq + q_off[i]);
+            } else {
+                J.row_off = (uint32_t)(S.base_rows + row_off[i]);
+                J.pred_base = (uint32_t)(S.base_preds + pred_off[i]);
+                J.spill_off = (uint32_t)(S.base_spill + spill_off[i]);
+                J.order_off = ~0ull;
+                stage_strip_job(jr, J, hq + q_off[i], hrec + row_off[i], hpr + pred_off[i], hsp + spill_off[i]);
+            }
         } else {
             PoaJob &J = hj[i];
             J.hf_off = hf_off[i] / (jr.kind == JK_WIDE ? 8 : 4);
             J.code_off = code_off[i] / (jr.kind == JK_WIDE ? 4 : 2);
             J.q_off = (uint32_t)q_off[i];
             J.row_off = (uint32_t)row_off[i];
-            J.pred_base = (uint32_t)pred_off[i];
+            J.pred_base = (uint32_t)(S.base_preds + pred_off[i]);
             J.aln_off = (uint32_t)aln_off[i];
             stage_job(jr, J, hq + q_off[i], hri + row_off[i], hrp + row_off[i], hpr + pred_off[i]);
         }
@@ -463,11 +498,13 @@ static void submit(rtl_ctx *ctx, PoaState &P, PoaSlot &S, std::vector<JobRef> &&
         CK(cudaMemcpyAsync(S.d_row_info.p, hri, rows_old * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(S.d_row_poff.p, hrp, rows_old * 4, cudaMemcpyHostToDevice, st));
     }
-    S.d_rec.need_geo(rows_strip + 1);
-    if (rows_strip) CK(cudaMemcpyAsync(S.d_rec.p, hrec, rows_strip * sizeof(uint4), cudaMemcpyHostToDevice, st));
-    S.d_spill.need_geo(spill_off[nj] + 1);
-    if (spill_off[nj]) CK(cudaMemcpyAsync(S.d_spill.p, hsp, spill_off[nj] * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(S.d_preds.need_geo(preds_total + 1), hpr, preds_total * 4, cudaMemcpyHostToDevice, st));
+    // (when the step has mirrored graphs, run_fold sized these buffers for the whole step: no reallocation here)
+    S.d_rec.need_geo(S.base_rows + rows_strip + 1);
+    if (rows_strip) CK(cudaMemcpyAsync(S.d_rec.p + S.base_rows, hrec, rows_strip * sizeof(uint4), cudaMemcpyHostToDevice, st));
+    S.d_spill.need_geo(S.base_spill + spill_off[nj] + 1);
+    if (spill_off[nj]) CK(cudaMemcpyAsync(S.d_spill.p + S.base_spill, hsp, spill_off[nj] * 4, cudaMemcpyHostToDevice, st));
+    S.d_preds.need_geo(S.base_preds + preds_total + 1);
+    if (preds_total) CK(cudaMemcpyAsync(S.d_preds.p + S.base_preds, hpr, preds_total * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(S.d_jobs.need_geo(nj), hj, nj * sizeof(PoaJob), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(S.d_sjobs.need_geo(nj), hsj, nj * sizeof(PoaSJob), cudaMemcpyHostToDevice, st));
     S.st.h2d_bytes += (int64_t)(q_off[nj] + rows_old * 8 + rows_strip * 16 + preds_total * 4 + spill_off[nj] * 4 +
@@ -501,7 +538,7 @@ static void submit(rtl_ctx *ctx, PoaState &P, PoaSlot &S, std::vector<JobRef> &&
             CK(cudaGetLastError());
             k_poa_strip_traceback<<<(cnt + 3) / 4, 128, 0, st>>>(S.d_sjobs.p + sg_.begin, cnt, S.d_rec.p, S.d_preds.p,
                                                                  S.d_spill.p, (const uint32_t *)S.arena, S.d_best.p + sg_.begin,
-                                                                 S.d_aln.p, S.d_aln_len.p + sg_.begin);
+                                                                 S.d_pool.p, S.d_aln.p, S.d_aln_len.p + sg_.begin);
             S.st.kernel_launches++;
         } else {
             const bool wide = sg_.key == 100 + JK_WIDE;
@@ -559,7 +596,7 @@ static void finish(rtl_ctx *ctx, PoaState &P, PoaSlot &S) {
         std::vector<std::pair<int32_t, int32_t>> aln((size_t)len);
         for (int x = 0; x < len; ++x) {  // reverse (sisd_alignment_engine.cpp:655) and map rows to node ids
             const int row = src[2 * (len - 1 - x)], pos = src[2 * (len - 1 - x) + 1];
-            aln[x].first = row < 0 ? -1 : g.rank_to_node[row - 1];
+            aln[x].first = row < 0 ? -1 : (jr.mirror ? row : g.rank_to_node[row - 1]);  // mirrored graphs: node ids
             aln[x].second = pos;
         }
         g.add_alignment(aln, jr.task->seq[jr.seq_index], jr.L);
@@ -580,6 +617,113 @@ static void finish(rtl_ctx *ctx, PoaState &P, PoaSlot &S) {
         }
     }
     S.jobs.clear();
+}
+
+// A graph leaves the device-mirror path (capacity exceeded, in-degree > 32, a read the strip kernel cannot take):
+// from now on the host sorts it itself.
+static void demote_mirror(PoaTask *t) {
+    t->mirror = false;
+    t->g.defer_sort = false;
+    if (!t->g.sorted) t->g.topological_sort();
+}
+
+// Step prologue for the graphs with a device mirror (`mj` = their indices in `all`): send the new entries of the
+// graphs' append logs, let the GPU fold them in, sort the graphs and build the row records (k_poa_graph_fold), and
+// read back how many rows each graph spills (the arena is divided with that).  `all` holds every job of the step: the
+// slot's d_rec / d_preds / d_spill are sized for all of them here, the mirrored graphs first.
+static void run_fold(rtl_ctx *ctx, PoaSlot &S, std::vector<JobRef> &all, const std::vector<size_t> &mj) {
+    (void)ctx;
+    const double ts0 = now_ms();
+    cudaStream_t st = S.stream;
+    const size_t nm = mj.size();
+    size_t rows_all = 0, preds_all = 0;
+    for (const auto &jr : all) {
+        rows_all += (size_t)jr.n + 1;
+        preds_all += jr.task->g.e_begin.size() + (size_t)jr.n;
+    }
+    std::vector<size_t> delta_off(nm + 1, 0);
+    size_t rows = 0, preds = 0;
+    DFoldJob *hf = S.h_fjobs.need_geo(nm);
+    for (size_t k = 0; k < nm; ++k) {
+        JobRef &jr = all[mj[k]];
+        PoaTask *t = jr.task;
+        const PoaGraph &g = t->g;
+        const int n_new = g.n_nodes(), e_new = (int)g.e_begin.size(), a_new = (int)g.a_node.size();
+        delta_off[k + 1] = delta_off[k] + dg_delta_words(n_new - t->sync_n, e_new - t->sync_e, a_new - t->sync_a);
+        jr.rec_off = (uint32_t)rows;
+        jr.pred_base = (uint32_t)preds;
+        jr.spill_off = (uint32_t)rows;  // one spill_rows entry per row is always enough
+        rows += (size_t)n_new + 1;
+        preds += (size_t)e_new + 4;
+        DFoldJob &F = hf[k];
+        F.gbase = t->gbase;
+        F.delta_off = (uint32_t)delta_off[k];
+        F.rec_off = jr.rec_off;
+        F.pred_base = jr.pred_base;
+        F.spill_off = jr.spill_off;
+        F.cap_n = t->cap_n;
+        F.cap_e = t->cap_e;
+        F.cap_a = t->cap_a;
+        F.n_old = t->sync_n;
+        F.n_new = n_new;
+        F.e_old = t->sync_e;
+        F.e_new = e_new;
+        F.a_old = t->sync_a;
+        F.a_new = a_new;
+        F.K = strip_ring_rows(strip_warps(jr.nst));
+        F.pad = 0;
+    }
+    if (delta_off[nm] >= (1ull << 32) || rows_all >= (1ull << 31) || preds_all + 4 * nm >= (1ull << 31))
+        throw CapacityError("POA step too large for 32-bit staging offsets");
+    S.base_rows = rows;
+    S.base_preds = preds;
+    S.base_spill = rows;
+    S.d_rec.need_geo(rows_all + 1);
+    S.d_preds.need_geo(preds_all + 4 * nm + 1);
+    S.d_spill.need_geo(rows_all + 1);
+    int32_t *hd = S.h_delta.need_geo(delta_off[nm] + 1);
+    const uint8_t *tab = letter_codes();
+    parallel_for(S.n_threads, nm, [&](size_t k) {
+        const JobRef &jr = all[mj[k]];
+        PoaTask *t = jr.task;
+        const PoaGraph &g = t->g;
+        const DFoldJob &F = hf[k];
+        int32_t *d = hd + delta_off[k];
+        const int dn = F.n_new - F.n_old;
+        if (dn) d[(dn - 1) / 4] = 0;
+        uint8_t *let = reinterpret_cast<uint8_t *>(d);
+        for (int v = F.n_old; v < F.n_new; ++v) let[v - F.n_old] = tab[(unsigned char)g.letter[v]];
+        int32_t *ed = d + (dn + 3) / 4;
+        for (int x = F.e_old; x < F.e_new; ++x) {
+            ed[2 * (x - F.e_old)] = g.e_begin[x];
+            ed[2 * (x - F.e_old) + 1] = g.e_end[x];
+        }
+        int32_t *al = ed + 2 * (F.e_new - F.e_old);
+        for (int x = F.a_old; x < F.a_new; ++x) {
+            al[2 * (x - F.a_old)] = g.a_owner[x];
+            al[2 * (x - F.a_old) + 1] = g.a_node[x];
+        }
+        t->sync_n = F.n_new;
+        t->sync_e = F.e_new;
+        t->sync_a = F.a_new;
+    });
+    CK(cudaMemcpyAsync(S.d_delta.need_geo(delta_off[nm] + 1), hd, delta_off[nm] * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(S.d_fjobs.need_geo(nm), hf, nm * sizeof(DFoldJob), cudaMemcpyHostToDevice, st));
+    S.d_counts.need_geo(2 * nm);
+    k_poa_graph_fold<<<(unsigned)((nm + 3) / 4), 128, 0, st>>>(S.d_fjobs.p, (int)nm, S.d_pool.p, S.d_delta.p,
+                                                           reinterpret_cast<uint32_t *>(S.d_rec.p), S.d_preds.p,
+                                                           S.d_spill.p, S.d_counts.p);
+    CK(cudaGetLastError());
+    int32_t *hc = S.h_counts.need_geo(2 * nm);
+    CK(cudaMemcpyAsync(hc, S.d_counts.p, 2 * nm * 4, cudaMemcpyDeviceToHost, st));
+    const double ts1 = now_ms();
+    CK(cudaStreamSynchronize(st));
+    S.t_wait += now_ms() - ts1;
+    S.t_stage += ts1 - ts0;
+    for (size_t k = 0; k < nm; ++k) all[mj[k]].n_spill = hc[2 * k];
+    S.st.kernel_launches++;
+    S.st.h2d_bytes += (int64_t)(delta_off[nm] * 4 + nm * sizeof(DFoldJob));
+    S.st.d2h_bytes += (int64_t)(2 * nm * 4);
 }
 
 // One unit's chain: its tasks advance in lock-step on slot `unit`, synchronously (the calling thread is the unit's
@@ -611,6 +755,37 @@ void poa_chain(rtl_ctx *ctx, int unit, std::vector<PoaTask *> &tasks, int sm, in
         t->acgtu = ok;
     }
     const int maxabs = std::max(std::max(std::abs(sm), std::abs(sn)), std::max(std::abs(sg), std::abs(se)));
+    // Device mirrors (poa_devgraph.cuh) for the graphs whose every read the strip kernel can take: the GPU then sorts
+    // the graph and builds the row records, the host only runs add_alignment.  Capacities are generous multiples of the
+    // longest read; a graph that outgrows them (or meets in-degree > 32) is demoted to the host path.
+    {
+        const bool want = ctx->poa_gpu_sort != 0 && ctx->poa_kernel != 1 && sm == 5 && sn == -4 && sg == -8 && se == -6;
+        size_t words = 0;
+        const size_t budget_words = (size_t)6 << 28;  // 6 GB of mirrors per unit at most
+        for (auto *t : tasks) {
+            t->mirror = false;
+            t->sync_n = t->sync_e = t->sync_a = 0;
+            if (!want || !t->acgtu) continue;
+            int maxlen = 0;
+            long long total = 0;
+            for (int l : t->len) {
+                maxlen = std::max(maxlen, l);
+                total += l;
+            }
+            if (maxlen == 0 || (int64_t)maxabs * (maxlen + 16) >= 32000) continue;
+            const long long cn = std::min<long long>(total + 8, 6ll * maxlen + 2048);
+            const size_t w = dg_words((int)cn, (int)(3 * cn), (int)(4 * cn));
+            if (words + w > budget_words) continue;
+            t->mirror = true;
+            t->cap_n = (int)cn;
+            t->cap_e = (int)(3 * cn);
+            t->cap_a = (int)(4 * cn);
+            t->gbase = words;
+            t->g.defer_sort = true;
+            words += w;
+        }
+        if (words) S.d_pool.need(words);
+    }
     // the int16 strip kernel is compiled for RATTLE's scores (correct.cpp:395: 5,-4,-8,-6); other scores take the
     // int32 kernel, and option poa_kernel=1 forces it
     const bool strip_scores = ctx->poa_kernel != 1 && sm == 5 && sn == -4 && sg == -8 && se == -6;
@@ -646,9 +821,30 @@ void poa_chain(rtl_ctx *ctx, int unit, std::vector<PoaTask *> &tasks, int sm, in
             PoaTask *t = direct[i];
             t->g.add_alignment({}, t->seq[step], t->len[step]);
         });
+        // graphs with a device mirror: fold + sort + row records on the GPU; the others are sorted by the host
+        S.base_rows = S.base_preds = S.base_spill = 0;
+        std::vector<size_t> mj;
+        for (size_t k = 0; k < all.size(); ++k) {
+            JobRef &jr = all[k];
+            PoaTask *t = jr.task;
+            if (!t->mirror) continue;
+            const PoaGraph &g = t->g;
+            if (jr.kind != JK_STRIP || g.n_nodes() > t->cap_n || (int)g.e_begin.size() > t->cap_e ||
+                (int)g.a_node.size() > t->cap_a) {
+                demote_mirror(t);
+                continue;
+            }
+            jr.mirror = true;
+            mj.push_back(k);
+        }
+        if (!mj.empty()) run_fold(ctx, S, all, mj);
         parallel_for(S.n_threads, all.size(), [&](size_t k) {
             JobRef &jr = all[k];
             if (jr.kind != JK_STRIP) return;
+            if (jr.mirror) {
+                jr.hf_bytes = ps_hf_words(jr.n, jr.nst, jr.n_spill) * 4;
+                return;
+            }
             jr.n_spill = plan_spills(jr.task, strip_ring_rows(strip_warps(jr.nst)));
             if (jr.n_spill >= 65535) {  // spill slots are 16-bit in the row records
                 jr.kind = JK_NARROW;

@@ -16,6 +16,12 @@ struct PoaTask {
     rtl::PoaGraph g;
     bool acgtu = false;  // every letter is one of A,C,G,T,U (set by poa_chain)
     std::vector<int32_t> spill_slot;  // scratch of the strip kernel's staging (poa_engine.cu:plan_spills)
+    // device mirror of the graph (poa_devgraph.cuh; set up by poa_chain): block offset and capacities in the unit's pool,
+    // and how much of the graph's append logs the mirror has seen
+    bool mirror = false;
+    uint64_t gbase = 0;
+    int cap_n = 0, cap_e = 0, cap_a = 0;
+    int sync_n = 0, sync_e = 0, sync_a = 0;
     std::vector<std::vector<std::pair<int32_t, int32_t>>> alns;  // filled when keep_alns
 };
 

@@ -22,8 +22,8 @@ struct PoaGraph {
     std::vector<int32_t> n_in, n_al;
     // edges (append order = creation order; per-node lists keep that order)
     std::vector<int32_t> e_begin, e_end, e_next_in, e_next_out;
-    // aligned-node lists
-    std::vector<int32_t> a_node, a_next;
+    // aligned-node lists (a_owner[x] = the node whose list entry x belongs to: the append log the device mirror replays)
+    std::vector<int32_t> a_node, a_next, a_owner;
     // sequences
     std::vector<std::vector<int32_t>> paths;
     // topological order
@@ -32,14 +32,19 @@ struct PoaGraph {
     std::vector<uint8_t> mark, check;
     std::vector<int32_t> stack;
     int max_in_degree = 0;
+    // The rank order is kept on the GPU for graphs that have a device mirror (poa_devgraph.cuh): add_alignment then
+    // skips the sort, and msa() sorts once at the end.
+    bool defer_sort = false, sorted = true;
 
     int n_nodes() const { return (int)letter.size(); }
 
     void clear() {
         letter.clear(); in_head.clear(); in_tail.clear(); out_head.clear(); out_tail.clear(); al_head.clear();
         al_tail.clear(); n_in.clear(); n_al.clear(); e_begin.clear(); e_end.clear(); e_next_in.clear();
-        e_next_out.clear(); a_node.clear(); a_next.clear(); paths.clear(); rank_to_node.clear(); node_to_rank.clear();
+        e_next_out.clear(); a_node.clear(); a_next.clear(); a_owner.clear(); paths.clear(); rank_to_node.clear(); node_to_rank.clear();
         max_in_degree = 0;
+        defer_sort = false;
+        sorted = true;
     }
 
     int add_node(char c) {
@@ -64,7 +69,7 @@ struct PoaGraph {
 
     void add_aligned(int node, int other) {
         const int id = (int)a_node.size();
-        a_node.push_back(other); a_next.push_back(-1);
+        a_node.push_back(other); a_next.push_back(-1); a_owner.push_back(node);
         if (al_tail[node] < 0) al_head[node] = id; else a_next[al_tail[node]] = id;
         al_tail[node] = id;
         ++n_al[node];
@@ -91,7 +96,7 @@ struct PoaGraph {
         if (aln.empty()) {
             add_chain(seq, 0, len, path);
             paths.push_back(std::move(path));
-            topological_sort();
+            after_change();
             return;
         }
         int first_valid = -1, last_valid = -1;
@@ -140,11 +145,17 @@ struct PoaGraph {
         if (tail != -1) add_edge(head, tail);
         path.insert(path.end(), tail_path.begin(), tail_path.end());
         paths.push_back(std::move(path));
-        topological_sort();
+        after_change();
+    }
+
+    void after_change() {
+        if (defer_sort) sorted = false;
+        else topological_sort();
     }
 
     // graph.cpp:293-353
     void topological_sort() {
+        sorted = true;
         const int n = n_nodes();
         rank_to_node.clear();
         rank_to_node.reserve(n);
@@ -192,7 +203,8 @@ struct PoaGraph {
     }
 
     // graph.cpp:371-426 (without the consensus row)
-    void msa(std::vector<std::string> &dst) const {
+    void msa(std::vector<std::string> &dst) {
+        if (!sorted) topological_sort();
         const int n = n_nodes();
         std::vector<int32_t> col(n, 0);
         int ncol = 0;

@@ -49,6 +49,8 @@ struct PoaSJob {
     uint32_t aln_off;    // pairs, into the alignment output
     uint32_t spill_off;  // into spill_rows: row of every spill slot (slot 0 -> row 0)
     int32_t L, n, n_strips, n_spill, pad;
+    uint64_t order_off;  // int32 words into the graph-mirror pool: rank -> node id of this graph (poa_devgraph.cuh), or
+                         // ~0: the traceback reports rows and the host maps them
 };
 // Row record (16 B): x = letter code | n_pred << 8 | own spill slot << 16 (0 = row is not spilled),
 // y, z, w = predecessor words (n_pred <= 3) or y, z = the first two and w = offset of the full list in preds.
@@ -496,7 +498,8 @@ __global__ void __launch_bounds__(128) k_poa_strip_traceback(const PoaSJob *__re
                                                              const int32_t *__restrict__ preds,
                                                              const int32_t *__restrict__ spill_rows,
                                                              const uint32_t *__restrict__ arena,
-                                                             const int4 *__restrict__ best_in, int32_t *aln_out,
+                                                             const int4 *__restrict__ best_in,
+                                                             const int32_t *__restrict__ pool, int32_t *aln_out,
                                                              int32_t *aln_len) {
     const int lane = threadIdx.x & 31;
     const int jb = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -512,6 +515,9 @@ __global__ void __launch_bounds__(128) k_poa_strip_traceback(const PoaSJob *__re
     int32_t *out = aln_out + 2 * (size_t)J.aln_off;
     int cnt = 0;
     int i = b.y, j = b.z;
+    // graphs with a device mirror: report node ids (what Graph::add_alignment consumes) instead of rows
+    const int32_t *order = (J.order_off != ~0ull) ? pool + J.order_off : nullptr;
+    auto node_of = [&](int row) -> int { return order ? order[row - 1] : row; };
     auto code_at = [&](int row, int col) -> uint32_t {  // row >= 1, col >= 1
         const int jj = col - 1;
         const uint32_t wv = cd[((size_t)(row - 1) * nst + (jj >> 8)) * 128 + ((jj >> 3) & 31) * 4 + (jj & 3)];
@@ -532,7 +538,7 @@ __global__ void __launch_bounds__(128) k_poa_strip_traceback(const PoaSJob *__re
             const unsigned mk = __ballot_sync(0xffffffffu, chain);
             const int run = (mk == 0xffffffffu) ? 32 : (__ffs(~mk) - 1);
             if (lane < run) {
-                out[2 * (cnt + lane)] = ik;
+                out[2 * (cnt + lane)] = node_of(ik);
                 out[2 * (cnt + lane) + 1] = jk - 1;
             }
             cnt += run;
@@ -545,7 +551,7 @@ __global__ void __launch_bounds__(128) k_poa_strip_traceback(const PoaSJob *__re
             if (!(c0 & 1u)) break;  // H == 0
             if (!(c0 & 2u)) {       // diagonal
                 if (lane == 0) {
-                    out[2 * cnt] = i;
+                    out[2 * cnt] = node_of(i);
                     out[2 * cnt + 1] = j - 1;
                 }
                 ++cnt;
@@ -553,7 +559,7 @@ __global__ void __launch_bounds__(128) k_poa_strip_traceback(const PoaSJob *__re
                 j = j - 1;
             } else if (!(c0 & 4u)) {  // vertical; extend_up iff H == F[p][j]+e
                 if (lane == 0) {
-                    out[2 * cnt] = i;
+                    out[2 * cnt] = node_of(i);
                     out[2 * cnt + 1] = -1;
                 }
                 ++cnt;
@@ -564,7 +570,7 @@ __global__ void __launch_bounds__(128) k_poa_strip_traceback(const PoaSJob *__re
                         const uint32_t c2 = code_at(i, j);
                         const bool stop = ((c2 >> 4) & 3u) >= 1u;  // F == H[p][j]+g
                         if (lane == 0) {
-                            out[2 * cnt] = i;
+                            out[2 * cnt] = node_of(i);
                             out[2 * cnt + 1] = -1;
                         }
                         ++cnt;
