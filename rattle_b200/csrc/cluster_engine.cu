@@ -247,7 +247,7 @@ static void make_cut_table(double thr, std::vector<uint16_t> &cut) {
     cut[0] = 4097;
 }
 
-static const int JC_CAP_W = 4736;   // staged hashes per warp in k_join_count (12 warps x 18.5 KB)
+static const int JC_CAP_W = 1760;   // staged hashes (list B) per warp in k_join_count: 16 warps x 6.9 KB, 2 CTAs per SM
 static const int PH_CAP_C = 1024;   // matches per warp kept in shared memory in k_pair_heavy (8 warps x 20 KB)
 
 // join + heavy over the current task buffer
@@ -257,7 +257,7 @@ static void run_pair_kernels(rtl_ctx *ctx, ClusterState &S, const TaskView &tv, 
     ReadView R = view(S);
     const int64_t surv_cap = (int64_t)S.surv.cap;
     S.ev.begin(EV_JOIN, st);
-    k_join_count<<<ctx->n_sm, JC_THREADS, (size_t)(JC_THREADS / 32) * JC_CAP_W * 4, st>>>(
+    k_join_count<<<ctx->n_sm * 2, JC_THREADS, (size_t)(JC_THREADS / 32) * JC_CAP_W * 4, st>>>(
         tv, S.tasks.p, S.counters.p + 0, R, t_s, JC_CAP_W, S.surv.p, S.counters.p + 1, surv_cap, nmatch_out,
         S.flags.p + 1, S.counters.p + 4);
     CK(cudaGetLastError());

@@ -432,7 +432,7 @@ __device__ __forceinline__ long long join_range(const uint32_t *pa, const uint32
 
 // warp per task; survivors of the exact bound  k*n_common/min_len >= t_s  are appended to `surv`
 // as (task index | min(n_common, 2^32-1) << 32).
-constexpr int JC_THREADS = 384;  // 12 warps x 18.5 KB of staged hash lists
+constexpr int JC_THREADS = 512;  // 16 warps per CTA, 2 CTAs per SM, 6.9 KB of staged hashes (list B) per warp
 __global__ void __launch_bounds__(JC_THREADS) k_join_count(TaskView tv, const uint64_t *__restrict__ tasks,
                                                            const unsigned long long *n_tasks_p, ReadView R, double t_s,
                                                            int cap_w, uint64_t *surv, unsigned long long *n_surv,
@@ -452,13 +452,14 @@ __global__ void __launch_bounds__(JC_THREADS) k_join_count(TaskView tv, const ui
         const int n1 = la - R.k, n2 = lb - R.k;
         const uint32_t *A = R.kh[0] + R.koff(ar);
         const uint32_t *B = (strand ? R.kh[1] : R.kh[0]) + R.koff(br);
+        // Only list B is staged in shared memory: every lane walks a contiguous 1/32 of A (two or three cache lines,
+        // read once, L1-resident) but probes all over B.  Half the staging traffic and twice the warps per SM of
+        // staging both lists.
         const uint32_t *pa = A, *pb = B;
-        if (n1 + n2 <= cap_w) {
-            for (int i = lane; i < n1; i += 32) sw[i] = A[i];
-            for (int i = lane; i < n2; i += 32) sw[n1 + i] = B[i];
+        if (n2 <= cap_w) {
+            for (int i = lane; i < n2; i += 32) sw[i] = B[i];
             __syncwarp();
-            pa = sw;
-            pb = sw + n1;
+            pb = sw;
         }
         const int per = (n1 + 31) >> 5;
         const int a0 = min(n1, lane * per), a1 = min(n1, a0 + per);
