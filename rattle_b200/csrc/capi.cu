@@ -117,6 +117,9 @@ int rtl_set_option(rtl_ctx *ctx, const char *key, int64_t value) {
     } else if (k == "poa_units") {
         if (value < 0 || value > 16) return RTL_ERR_INPUT;
         ctx->poa_units = (int)value;
+    } else if (k == "poa_mirror_pct") {
+        if (value < 1 || value > 100) return RTL_ERR_INPUT;
+        ctx->poa_mirror_pct = (int)value;
     } else if (k == "poa_gpu_sort") {
         ctx->poa_gpu_sort = (int)value;
     } else if (k == "poa_kernel") {

@@ -312,7 +312,11 @@ static int strip_warps(int nst) {
 }
 // rows of the shared-memory ring for a CTA of nw warps: 6 where the register file limits the CTAs per SM anyway,
 // 5 for 6-warp CTAs, where one row less lets a fourth CTA fit into the SM's shared memory
-static int strip_ring_rows(int nw) { return nw == 6 ? 5 : PS_K; }
+static int strip_ring_rows(int nw) {
+    static const int force = getenv("RATTLE_B200_RING") ? atoi(getenv("RATTLE_B200_RING")) : 0;  // experiments
+    if (force >= 2 && force <= PS_K) return force;
+    return nw == 6 ? 5 : PS_K;
+}
 
 // strip kernel, step 1 (before the arena is divided): which rows must be spilled to HBM?  Row p is read from the
 // shared-memory ring by rows up to PS_K ranks later; if a successor is further away the row gets a spill slot
@@ -773,7 +777,8 @@ void poa_chain(rtl_ctx *ctx, int unit, std::vector<PoaTask *> &tasks, int sm, in
                 total += l;
             }
             if (maxlen == 0 || (int64_t)maxabs * (maxlen + 16) >= 32000) continue;
-            const long long cn = std::min<long long>(total + 8, 6ll * maxlen + 2048);
+            // (option poa_mirror_pct shrinks the capacity: tests use it to exercise the demotion to the host path)
+            const long long cn = std::max<long long>(16, std::min<long long>(total + 8, 6ll * maxlen + 2048) * ctx->poa_mirror_pct / 100);
             const size_t w = dg_words((int)cn, (int)(3 * cn), (int)(4 * cn));
             if (words + w > budget_words) continue;
             t->mirror = true;

@@ -187,3 +187,23 @@ def test_poa_int32_kernel_still_matches(ctx, ref):
     for a, b in zip(alns, ealns):
         assert np.array_equal(a, b)
     assert rows == erows
+
+
+@pytest.mark.parametrize("opt,val", [("poa_gpu_sort", 0), ("poa_mirror_pct", 12), ("poa_mirror_pct", 30)])
+def test_poa_host_sort_and_mirror_demotion(ctx, ref, opt, val):
+    """graphs sorted on the host (poa_gpu_sort=0), and graphs that outgrow a deliberately small device mirror in the
+    middle of the chain and are demoted to the host path (deferred sort caught up, records staged by the host)"""
+    rs = pack(13, 24, 500.0, p_sub=0.05, p_ins=0.03, p_del=0.03)
+    ctx.set_option(opt, val)
+    try:
+        rows, alns = ctx.poa_msa(rs.bases, rs.offsets, want_alignments=True)
+        cl = clusters_of([24])
+        out = ctx.correct_reads(rs.bases, rs.quals, rs.offsets, cl, min_reads=5)
+    finally:
+        ctx.set_option("poa_gpu_sort", 1)
+        ctx.set_option("poa_mirror_pct", 100)
+    erows, ealns = ref.poa_msa(rs.bases, rs.offsets, want_alignments=True)
+    for i, (a, b) in enumerate(zip(alns, ealns)):
+        assert np.array_equal(a, b), "alignment %d differs" % i
+    assert rows == erows
+    check_correct(out, ref.correct_reads(rs.bases, rs.quals, rs.offsets, cl.as_dict(), min_reads=5, n_threads=1))
