@@ -69,7 +69,9 @@ struct ClusterState {
     DevBuf<uint64_t> long_off, long_scratch;
     // wave state
     DevBuf<uint8_t> taken, owner_rev, is_seed;
-    DevBuf<int32_t> owner, item_read, cand, seed_item, wave;
+    DevBuf<int32_t> owner, item_read, item_rid, cand, seed_item, wave;
+    DevBuf<uint32_t> memo;      // known k-mer-test failures between representatives (cluster_kernels.cuh: Memo)
+    uint32_t rid_dim = 0;       // 0 = memo off
     DevBuf<uint32_t> best, acc;
     DevBuf<uint16_t> cut;
     DevBuf<uint64_t> tasks, surv;
@@ -298,7 +300,8 @@ static void ensure_work_buffers(rtl_ctx *ctx, ClusterState &S, int64_t M) {
 
 // One greedy pass (cluster.cpp:124-166 with items = reads, :174-245 with items = cluster representatives).
 // Result: owner[j] = item index of the seed that took item j (owner[j]==j for seeds), owner_rev[j] = rev flag.
-static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, double thr, bool both, double t_s, double t_v,
+static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const int32_t *h_item_rid, double thr, bool both,
+                        double t_s, double t_v,
                         std::vector<int32_t> &owner, std::vector<uint8_t> &owner_rev) {
     ClusterState &S = state(ctx);
     cudaStream_t st = ctx->stream;
@@ -310,6 +313,14 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, double 
         CK(cudaMemcpyAsync(S.item_read.p, h_item_read, (size_t)M * 4, cudaMemcpyHostToDevice, st));
         ctx->stats.h2d_bytes += (int64_t)M * 4;
         d_item_read = S.item_read.p;
+    }
+    Memo memo{};
+    if (h_item_rid && S.rid_dim) {
+        CK(cudaMemcpyAsync(S.item_rid.need(M), h_item_rid, (size_t)M * 4, cudaMemcpyHostToDevice, st));
+        ctx->stats.h2d_bytes += (int64_t)M * 4;
+        memo.item_rid = S.item_rid.p;
+        memo.bits = S.memo.p;
+        memo.rid_dim = S.rid_dim;
     }
     std::vector<uint16_t> cut;
     make_cut_table(thr, cut);
@@ -353,6 +364,7 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, double 
             a.rank = ctx->rank;
             a.world = ctx->world;
             a.ts_cap = BVS_TS;
+            a.memo = memo;
             a.tasks = S.tasks.p;
             a.n_tasks = S.counters.p;
             a.task_cap = (int64_t)S.tasks.cap;
@@ -365,7 +377,7 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, double 
             S.ev.end(EV_BV, st);
             ctx->stats.kernel_launches++;
             ctx->stats.bv_launches++;
-            TaskView tv{S.cand.p, S.cand.p, d_item_read};
+            TaskView tv{S.cand.p, S.cand.p, d_item_read, memo};
             Sink sink{};
             sink.mode = 1;
             sink.acc = S.acc.p;
@@ -399,6 +411,7 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, double 
             a.rank = ctx->rank;
             a.world = ctx->world;
             a.ts_cap = BVS_TS;
+            a.memo = memo;
             a.tasks = S.tasks.p;
             a.n_tasks = S.counters.p;
             a.task_cap = (int64_t)S.tasks.cap;
@@ -413,7 +426,7 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, double 
             S.ev.end(EV_BV, st);
             ctx->stats.kernel_launches++;
             ctx->stats.bv_launches++;
-            TaskView tv{S.seed_item.p, nullptr, d_item_read};
+            TaskView tv{S.seed_item.p, nullptr, d_item_read, memo};
             Sink sink{};
             sink.mode = 2;
             sink.best = S.best.p;
@@ -486,7 +499,7 @@ void cluster_run(rtl_ctx *ctx, int k, double t_s, double t_v, double bv_thr, dou
 
     std::vector<int32_t> owner;
     std::vector<uint8_t> orev;
-    greedy_pass(ctx, N, nullptr, bv_thr, both, t_s, t_v, owner, orev);
+    greedy_pass(ctx, N, nullptr, nullptr, bv_thr, both, t_s, t_v, owner, orev);
 
     std::vector<Cluster> cl;
     {
@@ -504,12 +517,31 @@ void cluster_run(rtl_ctx *ctx, int k, double t_s, double t_v, double bv_thr, dou
 
     double thr = bv_thr - bv_falloff;
     bool last = false;
-    std::vector<int32_t> rep;
+    std::vector<int32_t> rep, rep_rid;
+    // Memo of failed k-mer tests between representatives (cluster_kernels.cuh: Memo).  A read gets a compact id when
+    // it first becomes a representative; only clusters that absorbed others can change theirs, so there are fewer
+    // than 2 x (clusters after the initial pass) ids in total.
+    std::vector<int32_t> read_rid(N, -1);
+    int32_t next_rid = 0;
+    S.rid_dim = 0;
+    {
+        const uint64_t dim = 2 * (uint64_t)cl.size();
+        const uint64_t words = (dim * dim * 2 + 31) / 32;
+        if (dim > 0 && words * 4 <= (1ull << 30)) {
+            S.rid_dim = (uint32_t)dim;
+            CK(cudaMemsetAsync(S.memo.need(words), 0, words * 4, ctx->stream));
+        }
+    }
     while (thr >= bv_min || last) {
         const int M = (int)cl.size();
         rep.resize(M);
-        for (int i = 0; i < M; ++i) rep[i] = cl[i].main.id;
-        greedy_pass(ctx, M, rep.data(), thr, both, t_s, t_v, owner, orev);
+        rep_rid.resize(M);
+        for (int i = 0; i < M; ++i) {
+            rep[i] = cl[i].main.id;
+            if (read_rid[rep[i]] < 0) read_rid[rep[i]] = next_rid++;
+            rep_rid[i] = read_rid[rep[i]];
+        }
+        greedy_pass(ctx, M, rep.data(), rep_rid.data(), thr, both, t_s, t_v, owner, orev);
         std::vector<Cluster> next;
         std::vector<int32_t> slot(M, -1);
         for (int i = 0; i < M; ++i)

@@ -198,10 +198,42 @@ __global__ void k_lengths(const uint64_t *__restrict__ off, int32_t *len, uint32
 // task = t (bits 0..31) | strand (bit 32) | s (bits 33..63)
 //   s indexes `seed_item` (or is the item itself), t indexes `tgt_list` (or is the item itself);
 //   items map to reads through `item_read` (or are reads themselves).
+// Merge rounds (items = clusters, compared through their representative reads): cluster_together(a, b, thr) is a pure
+// function of the two reads whose k-mer test does not depend on thr (cluster.cpp:24-37,48-61), and the merge rounds
+// compare the same surviving representatives again at every threshold (cluster.cpp:171-255).  `memo` remembers the
+// (seed representative, target representative, strand) triples whose k-mer test failed: bit
+// ((rid_a * rid_dim + rid_b) * 2 + strand), rid = compact id of a read that is or was a representative.  The scan drops
+// such pairs instead of emitting a task — the outcome ("no match") is known.
+struct Memo {
+    const int32_t *item_rid;  // nullable: no memo (initial pass over reads, function-level entry points)
+    uint32_t *bits;
+    uint32_t rid_dim;
+    __device__ __forceinline__ bool known_failure(uint32_t a_item, uint32_t b_item, int strand) const {
+        if (!item_rid) return false;
+        const uint32_t ra = (uint32_t)item_rid[a_item], rb = (uint32_t)item_rid[b_item];
+        if (ra >= rid_dim || rb >= rid_dim) return false;
+        const uint64_t bit = ((uint64_t)ra * rid_dim + rb) * 2 + (uint32_t)strand;
+        return (bits[bit >> 5] >> (bit & 31)) & 1u;
+    }
+    __device__ __forceinline__ void record_failure(uint32_t a_item, uint32_t b_item, int strand) const {
+        if (!item_rid) return;
+        const uint32_t ra = (uint32_t)item_rid[a_item], rb = (uint32_t)item_rid[b_item];
+        if (ra >= rid_dim || rb >= rid_dim) return;
+        const uint64_t bit = ((uint64_t)ra * rid_dim + rb) * 2 + (uint32_t)strand;
+        atomicOr(&bits[bit >> 5], 1u << (bit & 31));
+    }
+};
+
 struct TaskView {
     const int32_t *seed_item;
     const int32_t *tgt_list;
     const int32_t *item_read;
+    Memo memo;
+    __device__ __forceinline__ void items(uint64_t task, uint32_t &a_item, uint32_t &b_item) const {
+        const uint32_t t = (uint32_t)task, s = (uint32_t)(task >> 33);
+        a_item = seed_item ? (uint32_t)seed_item[s] : s;
+        b_item = tgt_list ? (uint32_t)tgt_list[t] : t;
+    }
     __device__ __forceinline__ void decode(uint64_t task, uint32_t &a_read, uint32_t &b_read, int &strand) const {
         uint32_t t = (uint32_t)task;
         strand = (int)((task >> 32) & 1);
@@ -238,6 +270,7 @@ struct BvScanArgs {
     int order_check;           // require seed item < target item
     int rank, world;           // target sharding
     int ts_cap;                // seeds per tile the shared memory is sized for (<= BVS_TS; fewer seeds -> more CTAs/SM)
+    Memo memo;                 // known k-mer-test failures between representatives (merge rounds)
     uint64_t *tasks;
     unsigned long long *n_tasks;
     int64_t task_cap;
@@ -298,7 +331,9 @@ __global__ void __launch_bounds__(BVS_THREADS) k_bv_scan(BvScanArgs A) {
         if (x >= n_t) return p;
         p.tslot = A.tgt_list ? x : A.t0 + x;  // value stored in the task
         p.item = A.tgt_list ? A.tgt_list[x] : p.tslot;
-        if (A.world > 1 && (p.item % A.world) != A.rank) return p;
+        // multi-GPU: targets are sharded by a key that is stable over the merge rounds (the representative's compact
+        // id), so that a rank meets the pairs it has memoised again
+        if (A.world > 1 && ((A.memo.item_rid ? A.memo.item_rid[p.item] : p.item) % A.world) != A.rank) return p;
         const bool taken = A.taken ? (A.taken[p.item] != 0) : false;
         p.rd = A.item_read ? (uint32_t)A.item_read[p.item] : (uint32_t)p.item;
         p.live = !taken;
@@ -357,6 +392,8 @@ __global__ void __launch_bounds__(BVS_THREADS) k_bv_scan(BvScanArgs A) {
                 const uint32_t cutv = A.cut[mmax];
                 pf = cf >= cutv;
                 pr = A.both && cr >= cutv;
+                if (pf && A.memo.known_failure((uint32_t)sitem[s], (uint32_t)item, 0)) pf = false;
+                if (pr && A.memo.known_failure((uint32_t)sitem[s], (uint32_t)item, 1)) pr = false;
             }
             my_pairs += (unsigned long long)__popc(__ballot_sync(0xffffffffu, valid));
             if (A.dense_common) {
@@ -471,6 +508,11 @@ __global__ void __launch_bounds__(JC_THREADS) k_join_count(TaskView tv, const ui
             if (nmatch_out) nmatch_out[ti] = cnt;
             const double mn = (double)min(la, lb);
             const double bound = (double)((long long)R.k * cnt) / mn;
+            if (!(bound >= t_s)) {
+                uint32_t ai, bi;
+                tv.items(tasks[ti], ai, bi);
+                tv.memo.record_failure(ai, bi, strand);
+            }
             if (bound >= t_s) {
                 unsigned long long idx = atomicAdd(n_surv, 1ull);
                 if ((long long)idx < surv_cap)
@@ -657,6 +699,11 @@ __global__ void __launch_bounds__(PH_THREADS) k_pair_heavy(TaskView tv, const ui
                 S.n_dist[ti] = nd;
                 S.var[ti] = v;
                 S.accept[ti] = ok ? 1 : 0;
+            }
+            if (!ok) {
+                uint32_t ai, bi;
+                tv.items(task, ai, bi);
+                tv.memo.record_failure(ai, bi, strand);
             }
             if (ok) {
                 const uint32_t t = (uint32_t)task;
