@@ -4,12 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--genes G]
 
 A "step" is one full pass of the hot path over the workload: k-mer extraction, the greedy bitvector/k-mer
-clustering (initial pass + merge rounds) and, with --correct (default once built), POA correction of the
-resulting clusters.  `value` is measured with the reads already resident in HBM (rtl_reads_upload done before
-the timed region); `e2e` goes through the reference-shaped C-ABI call with HOST buffers (H2D of the reads and D2H
-of the cluster set / FASTQ text inside the timed region).  N>1 (torchrun): the (seed,target) pair evaluation of
-every greedy wave is sharded over ranks by target index with one NCCL min-allreduce of the decision arrays
-per wave phase; clusters are sharded over ranks for correction (no collective).
+clustering (initial pass + merge rounds) and POA correction of the resulting clusters (--no-correct: clustering
+only).  `value` is measured with the reads already resident in HBM (rtl_reads_upload done before the timed region);
+`e2e` goes through the reference-shaped C-ABI call with HOST buffers (H2D of the reads and D2H of the cluster set /
+FASTQ text inside the timed region).  N>1 (torchrun) is WEAK scaling: N GPUs cluster and correct N x 100 k reads;
+the (seed,target) pair evaluation of every greedy wave is sharded over ranks with one NCCL min-allreduce of the
+decision arrays per wave phase, and clusters are sharded over ranks for correction (no collective).
 
 --impl reference times the UNMODIFIED reference (oracle/_ref/libref_shim.so, compiled from /root/reference) on the
 host cores, on a bounded sample of the same workload.

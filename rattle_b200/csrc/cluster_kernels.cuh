@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(PH_THREADS) k_pair_heavy(TaskView tv, const ui
 // wave state (device): [0]=cursor, [1]=n_cand, [2]=n_seeds, [3]=done flag
 // k_select: one CTA scans items from the cursor and takes the first W untaken ones as this wave's candidates.
 __global__ void k_select(uint8_t *taken, int M, int W, int32_t *cand, int32_t *wave) {
-    __shared__ int s_count, s_base;
+    __shared__ int s_count;
     const int tid = threadIdx.x, nt = blockDim.x;
     int cursor = wave[0];
     if (tid == 0) s_count = 0;
@@ -737,7 +737,6 @@ __global__ void k_select(uint8_t *taken, int M, int W, int32_t *cand, int32_t *w
         __syncthreads();
         if (tid == 0) {
             int run = s_count;
-            s_base = run;
             for (int i = 0; i < (nt >> 5); ++i) {
                 int c = wcnt[i];
                 wcnt[i] = run;

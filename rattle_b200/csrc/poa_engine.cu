@@ -291,18 +291,19 @@ static void stage_job(const JobRef &jr, PoaJob &J, uint8_t *q, uint32_t *row_inf
 
 // letter -> code of the strip kernel's score profile (255 = not representable: the int32 kernel takes the job)
 static const uint8_t *letter_codes() {
-    static uint8_t tab[256];
-    static bool init = false;
-    if (!init) {
-        memset(tab, 255, sizeof(tab));
-        tab[(unsigned char)'A'] = 0;
-        tab[(unsigned char)'C'] = 1;
-        tab[(unsigned char)'G'] = 2;
-        tab[(unsigned char)'T'] = 3;
-        tab[(unsigned char)'U'] = 4;
-        init = true;
-    }
-    return tab;
+    struct Table {
+        uint8_t v[256];
+        Table() {
+            memset(v, 255, sizeof(v));
+            v[(unsigned char)'A'] = 0;
+            v[(unsigned char)'C'] = 1;
+            v[(unsigned char)'G'] = 2;
+            v[(unsigned char)'T'] = 3;
+            v[(unsigned char)'U'] = 4;
+        }
+    };
+    static const Table t;  // thread-safe initialisation: unit threads call this concurrently
+    return t.v;
 }
 
 // strip kernel: warps per CTA = strips per pass, passes balanced (9 strips -> 2 passes of 5 and 4, not 8 and 1)
