@@ -71,3 +71,13 @@ def test_world2_exchange_and_sharding():
         assert members == list(range(25))
         assert got[0][0] == [0, 2, 4, 6] and got[1][0] == [1, 3, 5]
         assert got[1][2] == [0, 1, 2, 11]
+
+
+def test_allreduce_callback_refuses_the_default_stream():
+    """The NCCL exchange must be enqueued on the stream the library runs on; handle 0 (the legacy default stream) would
+    silently fall back to the library's own non-blocking stream, which the default stream does not order against
+    (this raced on 2 x B200 before the callback took the stream explicitly)."""
+    import pytest
+    from rattle_b200.dist import make_allreduce_callback
+    with pytest.raises(ValueError):
+        make_allreduce_callback(0)
