@@ -41,15 +41,22 @@ def test_no_gpu_means_loud_failure():
 
 def test_product_never_uses_the_oracle():
     bad = []
-    for dp, _, files in os.walk(os.path.join(ROOT, "rattle_b200")):
-        if "build" in dp.split(os.sep):
-            continue
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
-                txt = open(os.path.join(dp, f), errors="ignore").read()
-                if re.search(r"import\s+oracle|from\s+oracle|liboracle|libref_shim|rattle_oracle\.h|orc_[a-z_]+\(", txt):
-                    bad.append(f)
+    for top in ("rattle_b200", "integration", "include"):  # the library, the drop-in CLI shim, the ABI
+        for dp, _, files in os.walk(os.path.join(ROOT, top)):
+            if "build" in dp.split(os.sep) or "_build" in dp.split(os.sep):
+                continue
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"import\s+oracle|from\s+oracle|liboracle|libref_shim|rattle_oracle\.h|orc_[a-z_]+\(|oracle/", txt):
+                        bad.append(os.path.join(top, f))
     assert not bad, bad
+    # the drop-in CLI links the library and the reference's main/fasta/utils objects only: no spoa, no reference kernels
+    dropin = os.path.join(ROOT, "integration", "_build", "rattle")
+    if os.path.exists(dropin):
+        out = subprocess.run(["nm", "-C", "--defined-only", dropin], capture_output=True, text=True).stdout
+        assert "spoa::" not in out and "extract_kmers_from_read" not in out and "cluster_together" not in out
+        assert "rattle_b200" in subprocess.run(["ldd", dropin], capture_output=True, text=True).stdout
     # and the shared library has no dependency on them
     import rattle_b200
     out = subprocess.run(["ldd", rattle_b200.lib_path()], capture_output=True, text=True).stdout
