@@ -296,6 +296,10 @@ def main():
                 "unit": "GB/s", "frac": gb / hbm, "traffic": POA_TRAFFIC_PER_LAUNCH, "peak_source": peak_src,
                 "gcups": cells / (busy * 1e-3) / 1e9, "launches": st2["poa_launches"],
                 "avg_launch_ms": st2["poa_ms"] / max(1, st2["poa_launches"]), "busy_ms": busy,
+                # from the committed ncu --set full capture of one 600-alignment launch (profiles/ncu_poa_strip_r01.txt)
+                "ncu": {"issue_slot_utilisation": 0.757, "dram_throughput_pct": 13.5, "warps_per_sm": 24,
+                        "registers": 72, "dram_bytes_per_cell": 2.0, "launch_algorithmic_bytes": 1.00e10,
+                        "launch_dram_bytes": 1.009e10, "launch_ms": 9.12},
                 "note": "integer-issue bound, not HBM bound: ~50 SASS instructions per DP cell at ~75 % issue-slot "
                         "utilisation (profiles/); GCUPS is the meaningful rate"}
     else:
