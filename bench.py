@@ -214,7 +214,8 @@ def main():
         else:
             from rattle_b200.dist import shard_clusters
             sub, _ = shard_clusters(cl, rank, world)
-        return ctx.correct_reads(bases_np, quals_np, rs.offsets, sub, **CORRECT_KW)
+        # results stay in the Context's host buffers (what the C ABI wrote): no copy into Python bytes objects
+        return ctx.correct_reads(bases_np, quals_np, rs.offsets, sub, as_bytes=False, **CORRECT_KW)
 
     def step_resident():
         cl = ctx.cluster_resident(**CLUSTER_KW)

@@ -285,8 +285,12 @@ class Context:
         return rows
 
     def correct_reads(self, bases, quals, offsets, clusters: ClusterSet, min_occ=0.3, gap_occ=0.3, err_ratio=30.0,
-                      split=200, min_reads=5, headers=None):
-        """correct_reads (correct.hpp:44): returns (corrected, uncorrected, consensi) FASTQ text as bytes."""
+                      split=200, min_reads=5, headers=None, as_bytes=True):
+        """correct_reads (correct.hpp:44): returns (corrected, uncorrected, consensi) FASTQ text as bytes.
+
+        as_bytes=False returns uint8 views of the Context's (reused) output buffers instead: they are what the library
+        wrote into caller-owned host memory, valid until the next correct_reads call on this Context — no extra copy
+        into Python bytes objects and no fresh pages to fault in on every call (bench.py's timed loop)."""
         bases = _bases(bases)
         quals = _bases(quals)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
@@ -302,7 +306,11 @@ class Context:
             hdr = np.frombuffer(b"".join(headers), dtype=np.uint8).copy()
         cap = 4 * int(offsets[-1]) + 256 * (n + nc) + 1024
         while True:
-            bufs = [np.empty(cap, np.uint8) for _ in range(3)]  # untouched pages cost nothing
+            held = getattr(self, "_corr_bufs", None)
+            if held is None or len(held[0]) < cap:
+                held = self._corr_bufs = [np.empty(cap, np.uint8) for _ in range(3)]  # untouched pages cost nothing
+            bufs = held
+            cap = len(bufs[0])
             lens = [c_i64(cap) for _ in range(3)]
             args = [self.h, _ptr(bases), _ptr(quals), _ptr(offsets), n, _ptr(hdr), _ptr(hoff), _ptr(clusters.main_id),
                     _ptr(clusters.main_rev), _ptr(gm), _ptr(clusters.cl_off), _ptr(clusters.mem_id),
@@ -314,7 +322,8 @@ class Context:
                 cap = max(l.value for l in lens) + 1024
                 continue
             self._check(rc)
-            return tuple(b[:l.value].tobytes() for b, l in zip(bufs, lens))
+            views = tuple(b[:l.value] for b, l in zip(bufs, lens))
+            return tuple(v.tobytes() for v in views) if as_bytes else views
 
 
 def hps_encode(cl: ClusterSet) -> bytes:

@@ -90,3 +90,50 @@ def test_hps_known_bytes():
     assert rattle_b200.hps_encode(cl).hex().startswith("01d019000102d0190001fe110001")
     head = bytes.fromhex("a204")  # varint 546
     assert int(head[0] & 0x7f) | (head[1] << 7) == 546
+
+
+def test_correct_reads_wrapper_buffers_with_a_mock_library():
+    """rattle_b200.Context.correct_reads without a GPU: the ctypes plumbing (buffer reuse, capacity retry, views vs
+    bytes) against a mock of rtl_correct_reads that fills the three caller buffers."""
+    import ctypes
+    import rattle_b200
+    from rattle_b200.api import Context
+
+    class Mock:
+        def __init__(self):
+            self.calls = 0
+            self.payload = [b"@r0\\nACGT\\n+\\nIIII\\n" * 3, b"", b"@gene_cluster_0 reads=3 labels=\\nACGT\\n+\\nKKKK\\n"]
+
+        def rtl_correct_reads(self, *args):
+            self.calls += 1
+            outs = args[-6:]
+            rc = 0
+            for i in range(3):
+                buf, ln = outs[2 * i], outs[2 * i + 1]._obj
+                need = len(self.payload[i])
+                if need > ln.value:
+                    rc = -3
+                else:
+                    ctypes.memmove(buf, self.payload[i], need)
+                ln.value = need
+            return rc
+
+        def rtl_last_error(self, h):
+            return b"mock"
+
+    ctx = object.__new__(Context)
+    ctx.L, ctx.h = Mock(), None
+    cl = rattle_b200.ClusterSet(np.array([0], np.int32), np.array([0], np.uint8), np.array([0, 3], np.int64),
+                                np.arange(3, dtype=np.int32), np.zeros(3, np.uint8))
+    bases = np.frombuffer(b"ACGT" * 3, np.uint8)
+    offs = np.array([0, 4, 8, 12], np.uint64)
+    out = ctx.correct_reads(bases, bases, offs, cl)
+    assert out == tuple(ctx.L.payload) and all(isinstance(x, bytes) for x in out)
+    first = ctx._corr_bufs
+    views = ctx.correct_reads(bases, bases, offs, cl, as_bytes=False)
+    assert ctx._corr_bufs is first  # buffers are reused
+    assert [v.tobytes() for v in views] == ctx.L.payload
+    ctx.L.payload[0] = b"x" * (len(first[0]) + 100)  # larger than the held buffers: one retry with the reported size
+    n = ctx.L.calls
+    views = ctx.correct_reads(bases, bases, offs, cl, as_bytes=False)
+    assert ctx.L.calls == n + 2 and len(views[0]) == len(ctx.L.payload[0])
