@@ -51,4 +51,4 @@ def test_device_graph_routines_match_host_graph(tmp_path):
         files.append(p)
     out = subprocess.run([exe] + files, capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "order mismatches 0, record mismatches 0" in out.stdout
+    assert "order mismatches 0, record mismatches 0, deferred-sort msa mismatches 0" in out.stdout
