@@ -165,6 +165,9 @@ __device__ __forceinline__ int dg_claim_u8(uint8_t *arr, int i) {
     const unsigned int old = atomicOr(w, 1u << sh);
     return (int)((old >> sh) & 0xffu);
 }
+#elif defined(CUDA_EMU)  // SIMT emulation on the host (tests/native/cuda_emu.h): lanes are real threads
+#define DG_ATOMIC_ADD(p, v) __atomic_fetch_add((p), (v), __ATOMIC_SEQ_CST)
+#define DG_ATOMIC_EXCH_U8(arr, i) ((int)__atomic_exchange_n((arr) + (i), (uint8_t)1, __ATOMIC_SEQ_CST))
 #else
 #define DG_ATOMIC_ADD(p, v) dg_host_add((p), (v))
 #define DG_ATOMIC_EXCH_U8(arr, i) dg_host_claim((arr), (i))
@@ -257,7 +260,7 @@ struct DFoldJob {
     int32_t K, pad;
 };
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(CUDA_EMU)
 // one warp per graph; counts[2*job] = spill slots, counts[2*job+1] = overflow predecessor words
 __global__ void __launch_bounds__(128) k_poa_graph_fold(const DFoldJob *__restrict__ jobs, int n_jobs, int32_t *pool,
                                                         const int32_t *__restrict__ delta, uint32_t *rec, int32_t *preds,

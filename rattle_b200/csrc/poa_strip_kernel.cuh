@@ -30,7 +30,9 @@
 // Eligibility (checked by the host, otherwise the int32 kernel runs): scores 5/-4/-8/-6 that fit int16, in-degree
 // <= 32, letters within {A,C,G,T,U}, fewer than 65535 spilled rows.
 #pragma once
+#ifndef CUDA_EMU  // tests/native/cuda_emu.h runs this source on the host (SIMT emulation, CPU tests)
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include <type_traits>
@@ -78,6 +80,9 @@ __device__ __forceinline__ int ps_hi(uint32_t v) { return ((int)v) >> 16; }
 __host__ __device__ constexpr uint32_t ps_pk(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 __host__ __device__ constexpr uint32_t ps_pk2(int v) { return ps_pk(v, v); }
 
+#ifndef CUDA_EMU
+using ps_saddr = uint32_t;  // 32-bit shared-space address
+#define PS_DYNAMIC_SHARED(type, name) extern __shared__ type name[]
 // volatile shared-memory accesses by 32-bit shared-space address (keeps the mailbox addresses in one register each)
 __device__ __forceinline__ unsigned long long ps_lds64(uint32_t addr) {
     unsigned long long v;
@@ -126,6 +131,34 @@ __device__ __forceinline__ uint4 ps_lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
     return v;
 }
+
+#else  // CUDA_EMU: "shared-space addresses" are plain pointers
+using ps_saddr = uintptr_t;
+#define PS_DYNAMIC_SHARED(type, name) type *name = reinterpret_cast<type *>(emu::g_smem)
+inline unsigned long long ps_lds64(ps_saddr a) { return __atomic_load_n(reinterpret_cast<unsigned long long *>(a), __ATOMIC_SEQ_CST); }
+inline void ps_sts64(ps_saddr a, unsigned long long v) { __atomic_store_n(reinterpret_cast<unsigned long long *>(a), v, __ATOMIC_SEQ_CST); }
+inline int ps_lds32(ps_saddr a) { return __atomic_load_n(reinterpret_cast<int *>(a), __ATOMIC_SEQ_CST); }
+inline void ps_sts32(ps_saddr a, int v) { __atomic_store_n(reinterpret_cast<int *>(a), v, __ATOMIC_SEQ_CST); }
+inline void ps_fetch_ring(ps_saddr s_row, ps_saddr s_halo, uint32_t (&cH)[4], uint32_t (&cF)[4], int &hl) {
+    memcpy(cH, reinterpret_cast<const void *>(s_row), 16);
+    memcpy(cF, reinterpret_cast<const void *>(s_row + 512), 16);
+    hl = ps_lds32(s_halo);
+}
+inline void ps_fetch_spilled(const uint32_t *g_row, const uint32_t *g_halo, uint32_t (&cH)[4], uint32_t (&cF)[4], int &hl) {
+    memcpy(cH, g_row, 16);
+    memcpy(cF, g_row + 128, 16);
+    hl = (int)*g_halo;
+}
+inline void ps_sts128(ps_saddr a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    const uint32_t v[4] = {x, y, z, w};
+    memcpy(reinterpret_cast<void *>(a), v, 16);
+}
+inline uint4 ps_lds128(ps_saddr a) {
+    uint4 v;
+    memcpy(&v, reinterpret_cast<const void *>(a), 16);
+    return v;
+}
+#endif
 
 // predecessor word of (row record, index) — records keep up to three predecessors inline
 __device__ __forceinline__ uint32_t ps_pred_word(const uint4 &rc, int idx, const int32_t *pr) {
@@ -190,7 +223,7 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
             unsigned int *job_counter, int K) {
     // dynamic: [warp][letter][lane] packed match/mismatch scores of the warp's strip, then [warp][PS_K][H 32 | F 32]
     // ring of recent rows, then [warp][8] ring of H left of the strip
-    extern __shared__ uint4 s_dyn[];
+    PS_DYNAMIC_SHARED(uint4, s_dyn);
     __shared__ unsigned long long s_mb[PS_MAXW][PS_D];
     __shared__ int s_done[PS_MAXW];
     __shared__ int s_job;
@@ -203,10 +236,10 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
     constexpr uint32_t one2 = 0x00010001u;
     constexpr int e8 = 8 * SE;
     // 32-bit shared-space addresses (one register each, no generic-address arithmetic in the row loop)
-    const uint32_t dyn_s = (uint32_t)__cvta_generic_to_shared(s_dyn);
-    const uint32_t prof_s = dyn_s + (uint32_t)((wid * PS_NLET * 32 + lane) * 16);             // + letter*512
-    const uint32_t ring_s = dyn_s + (uint32_t)((NW * PS_NLET * 32 + wid * K * 64 + lane) * 16);  // + idx*1024 (F +512)
-    const uint32_t hring_s = dyn_s + (uint32_t)(NW * (PS_NLET * 32 + K * 64) * 16 + wid * 32);   // + idx*4
+    const ps_saddr dyn_s = (ps_saddr)__cvta_generic_to_shared(s_dyn);
+    const ps_saddr prof_s = dyn_s + (uint32_t)((wid * PS_NLET * 32 + lane) * 16);             // + letter*512
+    const ps_saddr ring_s = dyn_s + (uint32_t)((NW * PS_NLET * 32 + wid * K * 64 + lane) * 16);  // + idx*1024 (F +512)
+    const ps_saddr hring_s = dyn_s + (uint32_t)(NW * (PS_NLET * 32 + K * 64) * 16 + wid * 32);   // + idx*4
 
     while (true) {
         if (tid == 0) s_job = (int)atomicAdd(job_counter, 1u);
@@ -272,10 +305,10 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                 uint32_t *cd_w = cd + (size_t)t * 128 + lane * 4;  // row r of the codes
                 const bool has_left = t > 0, has_right = t + 1 < nst;
                 const bool left_smem = pos > 0, right_smem = pos + 1 < NW;
-                const uint32_t mb_in = (uint32_t)__cvta_generic_to_shared(&s_mb[left_smem ? pos - 1 : 0][0]);
-                const uint32_t mb_out = (uint32_t)__cvta_generic_to_shared(&s_mb[pos][0]);
-                const uint32_t done_in = (uint32_t)__cvta_generic_to_shared(&s_done[pos]);
-                const uint32_t done_out = (uint32_t)__cvta_generic_to_shared(&s_done[right_smem ? pos + 1 : pos]);
+                const ps_saddr mb_in = (ps_saddr)__cvta_generic_to_shared(&s_mb[left_smem ? pos - 1 : 0][0]);
+                const ps_saddr mb_out = (ps_saddr)__cvta_generic_to_shared(&s_mb[pos][0]);
+                const ps_saddr done_in = (ps_saddr)__cvta_generic_to_shared(&s_done[pos]);
+                const ps_saddr done_out = (ps_saddr)__cvta_generic_to_shared(&s_done[right_smem ? pos + 1 : pos]);
                 const int lane_e8 = lane * e8;
                 int cdone = 0;  // rows the right neighbour is known to have consumed
                 int bestv = 0, bestr = 0;
@@ -341,7 +374,7 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                         // every lane polls the same word (broadcast read): no divergence, no shuffle
                         uint32_t payload;
                         if (left_smem) {
-                            const uint32_t slot = mb_in + (uint32_t)(r & (PS_D - 1)) * 8u;
+                            const ps_saddr slot = mb_in + (uint32_t)(r & (PS_D - 1)) * 8u;
                             unsigned long long v = ps_lds64(slot);
                             while ((uint32_t)(v >> 32) != (uint32_t)r) {
                                 __nanosleep(40);  // leave the issue slots to the warps that produce the row
