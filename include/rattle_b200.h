@@ -151,6 +151,13 @@ int rtl_correct_reads(rtl_ctx *ctx, const char *bases, const char *quals, const 
  * n_labels = 0 (the default) gives the reference's label-less headers ("labels="). */
 int rtl_set_labels(rtl_ctx *ctx, const char *const *labels, int n_labels);
 
+/* Sharded correction (independent clusters, no collective): a rank that corrects a SUBSET of the cluster
+ * set passes the subset to rtl_correct_reads and, here, the index each of those clusters has in the whole set — the id
+ * the reference writes into every header (",gene_cluster_<cid>", "@gene_cluster_<cid>", "@transcript_cluster_<cid>";
+ * correct.cpp:344-349,540-549).  Applies to the following rtl_correct_reads calls, which must pass n_clusters == n;
+ * n = 0 (the default) numbers the clusters 0..n_clusters-1. */
+int rtl_set_cluster_ids(rtl_ctx *ctx, const int32_t *ids, int n);
+
 /* -------------------------------------------------------------------------------- clusters.out codec */
 int64_t rtl_hps_encode(int n_clusters, const int32_t *main_id, const uint8_t *main_rev, const int32_t *main_gene,
                        const int64_t *cl_off, const int32_t *mem_id, const uint8_t *mem_rev,

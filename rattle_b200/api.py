@@ -38,7 +38,7 @@ ALLREDUCE_FN = ctypes.CFUNCTYPE(c_i, c_p, c_p, c_i64)
 # every symbol include/rattle_b200.h declares (tests/test_boundary.py checks the header against this list)
 SYMBOLS = ["rtl_init", "rtl_destroy", "rtl_last_error", "rtl_set_option", "rtl_set_stream", "rtl_get_stats", "rtl_cluster_reads",
            "rtl_reads_upload", "rtl_cluster_resident", "rtl_set_shard", "rtl_extract_kmers", "rtl_bv_scan",
-           "rtl_pair_similarity", "rtl_poa_msa", "rtl_correct_reads", "rtl_set_labels", "rtl_hps_encode", "rtl_hps_decode"]
+           "rtl_pair_similarity", "rtl_poa_msa", "rtl_correct_reads", "rtl_set_labels", "rtl_set_cluster_ids", "rtl_hps_encode", "rtl_hps_decode"]
 
 _lib = None
 
@@ -81,6 +81,8 @@ def load_library():
     L.rtl_extract_kmers.argtypes = [c_p, c_p, c_p, c_u32, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]
     L.rtl_set_labels.restype = c_i
     L.rtl_set_labels.argtypes = [c_p, c_p, c_i]
+    L.rtl_set_cluster_ids.restype = c_i
+    L.rtl_set_cluster_ids.argtypes = [c_p, c_p, c_i]
     L.rtl_bv_scan.restype = c_i
     L.rtl_bv_scan.argtypes = [c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_d, c_p, c_p]
     L.rtl_pair_similarity.restype = c_i
@@ -167,6 +169,14 @@ class Context:
         """file labels of `rattle correct -l` (consensus headers then carry per-label read counts)"""
         arr = (ctypes.c_char_p * max(1, len(labels)))(*[x.encode() if isinstance(x, str) else x for x in labels])
         self._check(self.L.rtl_set_labels(self.h, arr, len(labels)))
+
+    def set_cluster_ids(self, ids):
+        """global ids of the clusters passed to the following correct_reads calls (sharded correction); None resets"""
+        if ids is None or len(ids) == 0:
+            self._check(self.L.rtl_set_cluster_ids(self.h, None, 0))
+        else:
+            a = np.ascontiguousarray(ids, dtype=np.int32)
+            self._check(self.L.rtl_set_cluster_ids(self.h, _ptr(a), len(a)))
 
     def stats(self) -> dict:
         s = Stats()
@@ -285,7 +295,7 @@ class Context:
         return rows
 
     def correct_reads(self, bases, quals, offsets, clusters: ClusterSet, min_occ=0.3, gap_occ=0.3, err_ratio=30.0,
-                      split=200, min_reads=5, headers=None, as_bytes=True):
+                      split=200, min_reads=5, headers=None, as_bytes=True, cluster_ids=None):
         """correct_reads (correct.hpp:44): returns (corrected, uncorrected, consensi) FASTQ text as bytes.
 
         as_bytes=False returns uint8 views of the Context's (reused) output buffers instead: they are what the library
@@ -296,6 +306,11 @@ class Context:
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = len(offsets) - 1
         nc = clusters.n_clusters
+        # the C side reads these through raw pointers: enforce the dtypes of include/rattle_b200.h
+        clusters = ClusterSet(np.ascontiguousarray(clusters.main_id, np.int32), np.ascontiguousarray(clusters.main_rev, np.uint8),
+                              np.ascontiguousarray(clusters.cl_off, np.int64), np.ascontiguousarray(clusters.mem_id, np.int32),
+                              np.ascontiguousarray(clusters.mem_rev, np.uint8), clusters.main_gene, clusters.mem_gene)
+        self.set_cluster_ids(cluster_ids)
         gm = np.full(nc, -1, np.int32) if clusters.main_gene is None else np.ascontiguousarray(clusters.main_gene, np.int32)
         gs = (np.full(len(clusters.mem_id), -1, np.int32) if clusters.mem_gene is None
               else np.ascontiguousarray(clusters.mem_gene, np.int32))
@@ -331,8 +346,12 @@ def hps_encode(cl: ClusterSet) -> bytes:
     L = load_library()
     cap = 16 + 12 * (len(cl.mem_id) + 2 * cl.n_clusters)
     out = np.zeros(cap, np.uint8)
-    n = L.rtl_hps_encode(cl.n_clusters, _ptr(cl.main_id), _ptr(cl.main_rev), _ptr(cl.main_gene), _ptr(cl.cl_off),
-                         _ptr(cl.mem_id), _ptr(cl.mem_rev), _ptr(cl.mem_gene), _ptr(out), cap)
+    i32 = lambda a: None if a is None else np.ascontiguousarray(a, np.int32)  # noqa: E731
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)  # noqa: E731
+    main_id, mem_id, main_gene, mem_gene = i32(cl.main_id), i32(cl.mem_id), i32(cl.main_gene), i32(cl.mem_gene)
+    main_rev, mem_rev, cl_off = u8(cl.main_rev), u8(cl.mem_rev), np.ascontiguousarray(cl.cl_off, np.int64)
+    n = L.rtl_hps_encode(cl.n_clusters, _ptr(main_id), _ptr(main_rev), _ptr(main_gene), _ptr(cl_off),
+                         _ptr(mem_id), _ptr(mem_rev), _ptr(mem_gene), _ptr(out), cap)
     if n < 0:
         raise RattleError(-3, "hps buffer too small")
     return out[:n].tobytes()
@@ -378,5 +397,6 @@ def cluster_reads(bases, offsets, kmer_size, t_s, t_v, bv_threshold, min_bv_thre
 def correct_reads(clusters: ClusterSet, bases, quals, offsets, min_occ, gap_occ, err_ratio, split, min_reads,
                   n_threads=1, verbose=False, labels=None, headers=None):
     """Same argument meaning as the reference's correct_reads (correct.hpp:44)."""
+    _ctx().set_labels(list(labels or []))
     return _ctx().correct_reads(bases, quals, offsets, clusters, min_occ, gap_occ, err_ratio, split, min_reads,
                                 headers=headers)

@@ -141,6 +141,12 @@ int rtl_set_labels(rtl_ctx *ctx, const char *const *labels, int n_labels) {
     return RTL_OK;
 }
 
+int rtl_set_cluster_ids(rtl_ctx *ctx, const int32_t *ids, int n) {
+    if (!ctx || n < 0 || (n > 0 && !ids)) return RTL_ERR_STATE;
+    ctx->cluster_ids.assign(ids, ids + n);
+    return RTL_OK;
+}
+
 int rtl_set_stream(rtl_ctx *ctx, void *cuda_stream) {
     if (!ctx) return RTL_ERR_STATE;
     cudaSetDevice(ctx->device);

@@ -129,6 +129,7 @@ struct rtl_ctx {
     int poa_mirror_pct = 100;  // capacity of the device graph mirrors, percent of the default (tests)
     int poa_kernel = 0;        // 0 = int16 strip kernel where eligible, 1 = int32 kernel only
     int64_t poa_arena_mb = 0;  // 0 = 40 % of free device memory, at most 64 GB
+    std::vector<int32_t> cluster_ids;  // global ids of the clusters of the next rtl_correct_reads calls (rtl_set_cluster_ids)
     std::vector<std::string> labels;  // file labels of `rattle correct -l` (rtl_set_labels; correct.cpp:447-470,488-512)
     // sharding
     int rank = 0, world = 1;

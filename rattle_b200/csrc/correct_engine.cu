@@ -338,10 +338,15 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
             seen[id] = 1;
         }
     }
+    // sharded correction (rtl_set_cluster_ids): cluster c of this call is cluster out_cid(c) of the whole cluster set,
+    // and that id is what the headers carry (correct.cpp:344-349,540-549 write the index in clusters.out)
+    if (!ctx->cluster_ids.empty() && (int)ctx->cluster_ids.size() != n_clusters)
+        throw InputError("rtl_set_cluster_ids: id count differs from n_clusters");
+    auto out_cid = [&](int cid) { return ctx->cluster_ids.empty() ? cid : (int)ctx->cluster_ids[cid]; };
     auto suffix = [&](int cid) {
         const int gid = main_gene ? main_gene[cid] : -1;
-        return gid == -1 ? ",gene_cluster_" + std::to_string(cid)
-                         : ",gene_cluster_" + std::to_string(gid) + ",transcript_cluster_" + std::to_string(cid);
+        return gid == -1 ? ",gene_cluster_" + std::to_string(out_cid(cid))
+                         : ",gene_cluster_" + std::to_string(gid) + ",transcript_cluster_" + std::to_string(out_cid(cid));
     };
     if (!duplicates) {
         parallel_for(nthreads, packs.size(), [&](size_t pi) {
@@ -513,8 +518,8 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
         std::string labels_result;
         for (size_t i = 0; i < labels.size(); ++i) labels_result += labels[i] + ":" + std::to_string(label_counts[i]) + ",";
         const std::string head =
-            (gene_mode ? "@gene_cluster_" + std::to_string(cid) + " reads=" + std::to_string(total_reads) + " labels="
-                       : "@transcript_cluster_" + std::to_string(cid) + " gene_cluster_" + std::to_string(gid) + " reads=" +
+            (gene_mode ? "@gene_cluster_" + std::to_string(out_cid(cid)) + " reads=" + std::to_string(total_reads) + " labels="
+                       : "@transcript_cluster_" + std::to_string(out_cid(cid)) + " gene_cluster_" + std::to_string(gid) + " reads=" +
                              std::to_string(total_reads) + " labels=") +
             labels_result;
         if (it.size() > 1) {

@@ -59,3 +59,23 @@ def shard_clusters(cl, rank, world):
                      None if cl.main_gene is None else cl.main_gene[keep].copy(),
                      None if cl.mem_gene is None else cl.mem_gene[:total][mask].copy())
     return sub, np.nonzero(keep)[0]
+
+
+def fastq_records(text: bytes):
+    """4-line FASTQ records of a text as a list of bytes (without the trailing newline)"""
+    lines = bytes(text).split(b"\n")
+    return [b"\n".join(lines[i:i + 4]) for i in range(0, len(lines) - 1, 4)]
+
+
+def merge_consensi(parts):
+    """consensi.fq of the whole cluster set from the ranks' consensi texts: records in cluster-id order, which is the
+    order correct_reads emits them in (correct.cpp:488-556 walks the clusters in clusters.out order).  The id is the
+    one in the header ('@gene_cluster_<cid> ...' / '@transcript_cluster_<cid> ...'), i.e. the global id passed through
+    rtl_set_cluster_ids."""
+    recs = []
+    for p in parts:
+        for r in fastq_records(p):
+            head = r.split(b" ", 1)[0]
+            recs.append((int(head.rsplit(b"_", 1)[1]), r))
+    recs.sort(key=lambda x: x[0])
+    return b"".join(r + b"\n" for _, r in recs)

@@ -118,6 +118,9 @@ def test_correct_reads_wrapper_buffers_with_a_mock_library():
                 ln.value = need
             return rc
 
+        def rtl_set_cluster_ids(self, h, ids, n):
+            return 0
+
         def rtl_last_error(self, h):
             return b"mock"
 
@@ -137,3 +140,25 @@ def test_correct_reads_wrapper_buffers_with_a_mock_library():
     n = ctx.L.calls
     views = ctx.correct_reads(bases, bases, offs, cl, as_bytes=False)
     assert ctx.L.calls == n + 2 and len(views[0]) == len(ctx.L.payload[0])
+
+
+@pytest.mark.parametrize("name,n_clusters,gene_level", [("clusters_rna_1500.out", None, True),
+                                                       ("clusters_rna_iso_1500.out", None, False)])
+def test_hps_codec_on_reference_written_clusters_out(name, n_clusters, gene_level):
+    """clusters.out files WRITTEN BY THE REFERENCE CLI (oracle/_ref/rattle cluster [--iso] on the 1500-read fixture;
+    tests/golden/make_golden_big.py hps): decode -> encode reproduces the file byte for byte, and the decoded set is a
+    partition of read indices with gene ids as main.cpp:266-273 / :302-318 write them."""
+    import rattle_b200
+    path = os.path.join(ROOT, "tests", "golden", name)
+    buf = open(path, "rb").read()
+    cs = rattle_b200.hps_decode(buf)
+    assert rattle_b200.hps_encode(cs) == buf
+    assert cs.n_clusters > 100 and cs.cl_off[0] == 0 and cs.cl_off[-1] == len(cs.mem_id)
+    assert len(set(cs.mem_id.tolist())) == len(cs.mem_id)  # every read in exactly one cluster
+    for c in range(cs.n_clusters):
+        assert cs.main_id[c] in cs.mem_id[cs.cl_off[c]:cs.cl_off[c + 1]]
+    if gene_level:
+        assert (cs.main_gene == -1).all() and (cs.mem_gene == -1).all()
+    else:  # --iso: transcript clusters carry the id of the gene cluster they were split from
+        assert (cs.main_gene >= 0).all() and cs.main_gene.max() < cs.n_clusters
+        assert (np.diff(cs.main_gene) >= 0).all()
