@@ -1,20 +1,30 @@
 #!/usr/bin/env python
-"""bench.py — reads/s of RATTLE's cluster(+correct) hot path on synthetic cDNA reads (BASELINE.json metric).
+"""bench.py — reads/s of RATTLE's cluster+correct hot path on synthetic cDNA reads (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--genes G]
 
-A "step" is one full pass of the hot path over the workload: k-mer extraction, the greedy bitvector/k-mer
-clustering (initial pass + merge rounds) and POA correction of the resulting clusters (--no-correct: clustering
-only).  `value` is measured with the reads already resident in HBM (rtl_reads_upload done before the timed region);
-`e2e` goes through the reference-shaped C-ABI call with HOST buffers (H2D of the reads and D2H of the cluster set /
-FASTQ text inside the timed region).  N>1 (torchrun) is WEAK scaling: N GPUs cluster and correct N x 100 k reads;
-the (seed,target) pair evaluation of every greedy wave is sharded over ranks with one NCCL min-allreduce of the
-decision arrays per wave phase, and clusters are sharded over ranks for correction (no collective).
+A "step" is one full pass of the hot path over the workload through the reference-shaped C-ABI calls with HOST
+buffers: rtl_cluster_reads (H2D of the reads, k-mer extraction, greedy bitvector/k-mer clustering: initial pass +
+merge rounds, D2H of the cluster set) and rtl_correct_reads (POA correction + consensus of the resulting clusters,
+FASTQ text written to host buffers).  ONE timed loop gives both numbers:
+
+  e2e    reads / step time (host -> host, copies inside the timed region)
+  value  reads / (step time - device time of the H2D copy of the read set), i.e. with the reads already resident in
+         HBM; the copy is timed with its own CUDA events inside the library (rtl_stats.upload_ms)
+
+Workload: BASELINE.json configs[1] shape (tools/synth.config2: genes x 50 reads x ~1.5 kb, both strands) at 2500
+genes = 125 k reads PER GPU, weak scaling, so that 8 GPUs run the 1 M reads BASELINE.json's metric names
+(--genes 2000 = configs[1] itself, 100 k reads).  N>1 (torchrun): every greedy wave's (seed, target) pairs are
+sharded over the ranks with one NCCL min-allreduce of the decision arrays per wave phase; clusters are sharded over
+the ranks for correction (no collective).  After the timed loop the outputs are digested (cluster set, consensi.fq,
+corrected/uncorrected as order-independent multiset digests) and, for N>1, rank 0 re-runs the whole workload
+UNSHARDED once (untimed) and the digests must be equal — a sharded run that differs fails loudly.
 
 --impl reference times the UNMODIFIED reference (oracle/_ref/libref_shim.so, compiled from /root/reference) on the
-host cores, on a bounded sample of the same workload.
+host cores, on a bounded sample of the same generator sized to the box's core count.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -32,8 +42,6 @@ from tools import synth  # noqa: E402
 
 CLUSTER_KW = dict(kmer_size=10, t_s=0.2, t_v=1e6, bv_threshold=0.4, min_bv_threshold=0.2, bv_falloff=0.05,
                   repr_percentile=0.15, is_rna=False)  # main.cpp:200-221 defaults, cDNA (both strands)
-# dram__bytes_read+write of one k_poa_strip launch (600 alignments, ncu --set full, profiles/ncu_poa_strip_r01.txt)
-POA_TRAFFIC_PER_LAUNCH = 10.09e9
 CORRECT_KW = dict(min_occ=0.3, gap_occ=0.3, err_ratio=30.0, split=200, min_reads=5)  # main.cpp:396-402
 
 
@@ -100,6 +108,53 @@ def make_workload(genes):
     return rs.sorted_by_length()[0]  # main.cpp:254 sort_read_set
 
 
+# ------------------------------------------------------------------------------------------------ output digests
+def cluster_digest(cl):
+    """sha256 of the flat cluster set (same as tests/golden/make_golden_config2.py: the clusters.out content)"""
+    h = hashlib.sha256()
+    for a in (cl.main_id, cl.main_rev, cl.cl_off, cl.mem_id, cl.mem_rev):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def records(text):
+    lines = bytes(text).split(b"\n")
+    return [b"\n".join(lines[i:i + 4]) for i in range(0, len(lines) - 1, 4)]
+
+
+def multiset_sum(recs):
+    """order-independent digest of a multiset of FASTQ records that adds up over shards: sum of sha256(record) mod 2^256"""
+    s = 0
+    for r in recs:
+        s += int.from_bytes(hashlib.sha256(r).digest(), "big")
+    return s % (1 << 256)
+
+
+def correction_digests(parts):
+    """parts: per-rank (corrected, uncorrected, consensi) texts -> digests of the whole job's output"""
+    from rattle_b200.dist import merge_consensi
+    cons = merge_consensi([p[2] for p in parts])
+    return {"consensi_sha256": hashlib.sha256(cons).hexdigest(), "consensi_records": cons.count(b"\n") // 4,
+            "corrected_sum256": "%064x" % (sum(multiset_sum(records(p[0])) for p in parts) % (1 << 256)),
+            "uncorrected_sum256": "%064x" % (sum(multiset_sum(records(p[1])) for p in parts) % (1 << 256))}
+
+
+def golden_form_digests(out):
+    """the digest forms tests/golden/make_golden_big.py stores (N=1 only: needs every record on one rank)"""
+    return {"corrected_sorted": hashlib.sha256(b"\n".join(sorted(records(out[0])))).hexdigest(),
+            "uncorrected": hashlib.sha256(bytes(out[1])).hexdigest(),
+            "consensi": hashlib.sha256(bytes(out[2])).hexdigest()}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def ref_sample_genes(args):
+    """bounded CPU sample: ~20 s of reference work per step on this box (cluster ~quadratic, correct linear in reads)"""
+    if args.ref_genes > 0:
+        return args.ref_genes
+    cores = os.cpu_count() or 1
+    return int(min(2000, max(60, 15 * cores)))
+
+
 def reference_arm(args, rank, world):
     """Unmodified reference on the host cores (rank 0 only)."""
     if rank != 0:
@@ -110,10 +165,11 @@ def reference_arm(args, rank, world):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_shim.so was not built in the container"}))
         return
     ref = oracle.reference()
-    genes = args.ref_genes
+    genes = ref_sample_genes(args)
     rs = make_workload(genes)
-    sample = "config-2 shape at %d genes x 50 reads = %d reads (~1.5 kb cDNA), cluster%s with %d threads" % (
-        genes, rs.n, "+correct" if args.correct else "", cores)
+    sample = ("same generator at %d genes x 50 = %d reads (~1.5 kb cDNA), cluster%s, %d threads; sample sized to the "
+              "core count (15 genes per core) so that one step is ~20 s" % (genes, rs.n, "+correct" if args.correct else "",
+                                                                             cores))
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -128,20 +184,38 @@ def reference_arm(args, rank, world):
     v = rs.n / (ms / 1e3)
     line = {"impl": "reference", "metric": "reads/sec cluster+correct" if args.correct else "reads/sec cluster",
             "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/int32",
-            "data": "synthetic", "config": workload_config(args, rs.n, genes),
-            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference", "sample": sample},
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
+            "data": "synthetic", "config": workload_config(args, rs.n, genes, 1),
+            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference", "sample": sample,
+                             "full_config_one_off": full_config_reference()},
             "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def workload_config(args, n_reads, genes):
-    return {"workload": "BASELINE.json configs[1] per GPU: %d synthetic cDNA reads x ~1.5 kb (%d genes x 50 reads, 3/2/2%% "
-                        "sub/ins/del, random strand), k=10 gene clustering%s" % (n_reads, genes,
-                                                                               " + correct" if args.correct else ""),
+def full_config_reference():
+    """one-off run of the unmodified reference on the whole configs[1] workload (100 k reads), made in the build
+    container by tests/golden/make_golden_big.py (the reference cannot repeat it 25 times inside a bench run)"""
+    p = os.path.join(ROOT, "tests", "golden", "config2_2000_correct.json")
+    if not os.path.exists(p):
+        return None
+    g = json.load(open(p))
+    s = g["cluster_seconds"] + g["correct_seconds"]
+    return {"n_reads": g["n_reads"], "seconds": s, "reads_per_s": g["n_reads"] / s, "threads": g["threads"],
+            "where": "build container (tests/golden/config2_2000_correct.json)"}
+
+
+DTYPE = "int16x2 (POA DP) / u64 popcount + u32 k-mer hash (clustering)"
+
+
+def workload_config(args, n_reads, genes, world):
+    return {"workload": "BASELINE.json configs[1] shape, %d genes x 50 reads per GPU: %d synthetic cDNA reads x ~1.5 kb in "
+                        "total (3/2/2%% sub/ins/del, random strand), k=10 gene clustering%s%s" % (
+                            genes // max(1, world), n_reads, " + correct" if args.correct else "",
+                            "; = the 1 M reads of BASELINE.json's metric" if n_reads == 1000000 else ""),
             "n_reads": int(n_reads), "kmer_size": 10, "strands": 2, "l2": "inputs larger than L2 (k-mer lists + "
-            "bitvectors of the workload exceed 126 MB); no explicit flush", "parallelism": "pair-shard x%d" % args.gpus}
+            "bitvectors of the workload exceed 126 MB); no explicit flush",
+            "parallelism": "wave pairs sharded x%d + min-allreduce (cluster), clusters round-robin x%d (correct)" % (world, world)}
 
 
 def main():
@@ -150,12 +224,13 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--genes", type=int, default=2000,
-                    help="genes PER GPU: 2000 genes x 50 reads = 100 k reads (configs[1]) at N=1; N GPUs cluster and "
-                         "correct N x 100 k reads (weak scaling: 8 GPUs = 800 k reads, the size BASELINE.json's metric names)")
-    ap.add_argument("--ref-genes", type=int, default=400, help="size of the bounded CPU sample (x50 reads)")
-    ap.add_argument("--no-correct", dest="correct", action="store_false", default=None)
+    ap.add_argument("--genes", type=int, default=2500,
+                    help="genes PER GPU (x 50 reads): 2500 = 125 k reads per GPU, so that 8 GPUs run the 1 M reads of "
+                         "BASELINE.json's metric; 2000 = configs[1] itself (100 k reads)")
+    ap.add_argument("--ref-genes", type=int, default=0, help="size of the bounded CPU sample (x50 reads); 0 = 15 per core")
+    ap.add_argument("--no-correct", dest="correct", action="store_false", default=True)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="N>1: skip the unsharded re-run that the digests are compared with")
     ap.add_argument("--opt", action="append", default=[], help="library tunable key=value (rtl_set_option)")
     args = ap.parse_args()
 
@@ -164,14 +239,13 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        if args.correct is None:
-            args.correct = True
         reference_arm(args, rank, world)
         return
 
     import torch
     import torch.distributed as dist
     import rattle_b200
+    from rattle_b200.dist import make_allreduce_callback, shard_clusters
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -185,12 +259,9 @@ def main():
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
     ctx.set_stream(stream.cuda_stream)
-    if args.correct is None:
-        args.correct = True
-
+    allreduce_cb = make_allreduce_callback(stream.cuda_stream) if world > 1 else None
     if world > 1:
-        from rattle_b200.dist import make_allreduce_callback
-        ctx.set_shard(rank, world, make_allreduce_callback(stream.cuda_stream))
+        ctx.set_shard(rank, world, allreduce_cb)
 
     total_genes = args.genes * world
     rs = make_workload(total_genes)
@@ -205,71 +276,96 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def correct_shard(cl):
-        """clusters sharded round-robin over ranks (independent packs, no collective)"""
-        if not args.correct:
-            return None
-        if world == 1:
-            sub = cl
+    def correct_shard(cl, sharded=True):
+        """clusters sharded round-robin over ranks (independent packs, no collective); headers carry global ids"""
+        if world == 1 or not sharded:
+            sub, gids = cl, None
         else:
-            from rattle_b200.dist import shard_clusters
-            sub, _ = shard_clusters(cl, rank, world)
+            sub, gids = shard_clusters(cl, rank, world)
         # results stay in the Context's host buffers (what the C ABI wrote): no copy into Python bytes objects
-        return ctx.correct_reads(bases_np, quals_np, rs.offsets, sub, as_bytes=False, **CORRECT_KW)
+        return ctx.correct_reads(bases_np, quals_np, rs.offsets, sub, as_bytes=False, cluster_ids=gids, **CORRECT_KW)
 
-    def step_resident():
-        cl = ctx.cluster_resident(**CLUSTER_KW)
-        st = ctx.stats()
-        out = correct_shard(cl)
-        st2 = ctx.stats() if args.correct else None
-        return cl, st, st2, out
-
-    def step_e2e():
+    def step():
+        """one pass of the hot path, host buffers in, host buffers out"""
         cl = ctx.cluster_reads(bases_np, rs.offsets, **CLUSTER_KW)
         st = ctx.stats()
-        out = correct_shard(cl)
-        return cl, st, out
+        out, st2 = None, None
+        if args.correct:
+            out = correct_shard(cl)
+            st2 = ctx.stats()
+        return cl, st, st2, out
 
-    def timed(fn, steps, warmup, sampler=None):
-        res = None
-        for _ in range(warmup):
-            res = fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        stats = []
-        if sampler:
-            sampler.__enter__()
-        e0.record(stream)
-        for _ in range(steps):
-            res = fn()
-            stats.append(res)
-        e1.record(stream)
-        barrier()
-        if sampler:
-            sampler.__exit__()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / steps, stats
-
-    # ---- device-resident arm (`value`)
-    ctx.upload(bases_np, rs.offsets)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms_res, res_stats = timed(step_resident, args.steps, args.warmup, sampler)
+    if sampler:
+        sampler.__enter__()
+    res = []
+    e0.record(stream)
+    for _ in range(args.steps):
+        res.append(step())
+    e1.record(stream)
+    barrier()
+    if sampler:
+        sampler.__exit__()
+    ms_total = e0.elapsed_time(e1)
+    upload_ms = sum(r[1]["upload_ms"] for r in res)
+    t = torch.tensor([ms_total / args.steps, (ms_total - upload_ms) / args.steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e, ms_res = float(t[0].item()), float(t[1].item())
     clocks = sampler.summary() if sampler else None
-    # ---- end-to-end arm through the C ABI with host buffers
-    ms_e2e, e2e_stats = timed(step_e2e, args.steps, 1)
 
-    cl, st, st2, out = res_stats[-1]
-    e_cl, e_st, e_out = e2e_stats[-1]
-    launches = st["kernel_launches"] + (st2["kernel_launches"] if st2 else 0)
-    h2d = e_st["h2d_bytes"]
-    d2h = e_st["d2h_bytes"] + int(cl.n_clusters) * 13 + n_reads * 5
-    if args.correct and e_out is not None:
-        h2d += 2 * int(rs.offsets[-1])
-        d2h += sum(len(x) for x in e_out)
+    cl, st, st2, out = res[-1]
+    launches = sum(r[1]["kernel_launches"] + (r[2]["kernel_launches"] if r[2] else 0) for r in res)
+    h2d = st["h2d_bytes"] + (st2["h2d_bytes"] if st2 else 0)
+    d2h = st["d2h_bytes"] + int(cl.n_clusters) * 13 + n_reads * 5 + (st2["d2h_bytes"] if st2 else 0)
+
+    # ---- digests of the job's output (untimed): every rank holds the same cluster set and its share of the FASTQ texts
+    digests = {"clusters_sha256": cluster_digest(cl)}
+    mine = tuple(bytes(x) for x in out) if out is not None else None
+    if args.correct:
+        if world > 1:
+            # the corrected reads stay where they are: only their order-independent digest and the consensi travel
+            part = (multiset_sum(records(mine[0])), multiset_sum(records(mine[1])), mine[2])
+            parts = [None] * world if rank == 0 else None
+            dist.gather_object(part, parts, dst=0)
+            if rank == 0:
+                from rattle_b200.dist import merge_consensi
+                cons = merge_consensi([p[2] for p in parts])
+                digests.update({"consensi_sha256": hashlib.sha256(cons).hexdigest(), "consensi_records": cons.count(b"\n") // 4,
+                                "corrected_sum256": "%064x" % (sum(p[0] for p in parts) % (1 << 256)),
+                                "uncorrected_sum256": "%064x" % (sum(p[1] for p in parts) % (1 << 256))})
+        else:
+            digests.update(correction_digests([mine]))
+            digests["golden_form"] = golden_form_digests(mine)
+            gp = os.path.join(ROOT, "tests", "golden", "config2_%d_correct.json" % total_genes)
+            if os.path.exists(gp):  # the unmodified reference's digests of this very workload
+                g = json.load(open(gp))["digests"]
+                digests["equals_reference_golden"] = all(digests["golden_form"][k] == g[k] for k in digests["golden_form"])
+        gc = os.path.join(ROOT, "tests", "golden", "config2_%d.json" % total_genes)
+        if os.path.exists(gc):
+            digests["clusters_equal_reference_golden"] = json.load(open(gc))["sha256"] == digests["clusters_sha256"]
+    # ---- N>1: the sharded outputs must equal an unsharded run of the same workload (one untimed check step, rank 0)
+    if world > 1 and not args.no_check:
+        if rank == 0:
+            ctx.set_shard(0, 1, None)
+            t0 = time.perf_counter()
+            cl1 = ctx.cluster_reads(bases_np, rs.offsets, **CLUSTER_KW)
+            ref_d = {"clusters_sha256": cluster_digest(cl1)}
+            if args.correct:
+                o1 = correct_shard(cl1, sharded=False)
+                ref_d.update(correction_digests([tuple(bytes(x) for x in o1)]))
+            digests["unsharded_check_s"] = time.perf_counter() - t0
+            digests["equals_unsharded"] = all(digests.get(k) == v for k, v in ref_d.items())
+            if not digests["equals_unsharded"]:
+                print(json.dumps({"error": "sharded output differs from the unsharded run", "sharded": digests,
+                                  "unsharded": ref_d}), file=sys.stderr)
+                sys.stderr.flush()
+                os._exit(3)
+        dist.barrier()
 
     if rank != 0:
         dist.destroy_process_group()
@@ -282,27 +378,27 @@ def main():
     if st2:
         kern["poa"] = st2["poa_ms"]
     dom = max(kern, key=kern.get)
-    roof = None
     bv_alg_bytes = st["bv_pairs"] * (512 * S + 4)  # 512*S+4 bytes per (representative, read) comparison
     bv_gbs = bv_alg_bytes / (st["bv_ms"] * 1e-3) / 1e9 if st["bv_ms"] > 0 else 0.0
     if dom == "poa":
         cells = st2["poa_cells"]
         # Algorithmic bytes per DP cell: the 2-byte traceback code, written once (H/F rows stay in the
-        # shared-memory ring).  Units (concurrent launch groups) overlap on the device, so the denominator is the
+        # shared-memory ring).  Kernels of concurrently running units overlap on the device, so the denominator is the
         # device time with at least one POA launch group running (union of the groups' CUDA-event intervals,
-        # rtl_stats.poa_busy_ms), not the sum of the overlapping launch durations.
+        # rtl_stats.poa_busy_ms), not the sum of the overlapping launch durations; `traffic` is what the kernels of
+        # THIS step wrote by construction (codes + spilled rows, counted by the library), per launch like `achieved`.
         busy = max(st2["poa_busy_ms"], 1e-6)
         gb = cells * 2 / (busy * 1e-3) / 1e9
+        nl = max(1, st2["poa_launches"])
         roof = {"kernel": "k_poa_strip (+ k_poa_strip_traceback)", "bound": "hbm", "achieved": gb, "peak": hbm,
-                "unit": "GB/s", "frac": gb / hbm, "traffic": POA_TRAFFIC_PER_LAUNCH, "peak_source": peak_src,
+                "unit": "GB/s", "frac": gb / hbm, "traffic": st2["poa_dram_bytes"] / nl,
+                "traffic_source": "counted by the library from the launches of this step (codes + spilled rows); "
+                                  "profiles/ holds the ncu dram__bytes of a launch of the same shape",
+                "algorithmic_bytes_per_launch": cells * 2 / nl, "peak_source": peak_src,
                 "gcups": cells / (busy * 1e-3) / 1e9, "launches": st2["poa_launches"],
-                "avg_launch_ms": st2["poa_ms"] / max(1, st2["poa_launches"]), "busy_ms": busy,
-                # from the committed ncu --set full capture of one 600-alignment launch (profiles/ncu_poa_strip_r01.txt)
-                "ncu": {"issue_slot_utilisation": 0.757, "dram_throughput_pct": 13.5, "warps_per_sm": 24,
-                        "registers": 72, "dram_bytes_per_cell": 2.0, "launch_algorithmic_bytes": 1.00e10,
-                        "launch_dram_bytes": 1.009e10, "launch_ms": 9.12},
-                "note": "integer-issue bound, not HBM bound: ~50 SASS instructions per DP cell at ~75 % issue-slot "
-                        "utilisation (profiles/); GCUPS is the meaningful rate"}
+                "avg_launch_ms": st2["poa_ms"] / nl, "busy_ms": busy,
+                "note": "integer-issue bound, not HBM bound (profiles/): GCUPS against the issue ceiling is the "
+                        "meaningful rate; the HBM fraction is reported as SURVEY 8(d) defines it"}
     else:
         roof = {"kernel": "k_bv_scan", "bound": "hbm", "achieved": bv_gbs, "peak": hbm, "unit": "GB/s",
                 "frac": bv_gbs / hbm, "traffic": None, "peak_source": peak_src, "pairs": st["bv_pairs"],
@@ -313,27 +409,33 @@ def main():
         "metric": "reads/sec cluster+correct" if args.correct else "reads/sec cluster",
         "value": n_reads / (ms_res * 1e-3), "unit": "reads/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64/int32", "data": "synthetic",
-        "config": workload_config(args, n_reads, total_genes),
+        "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": workload_config(args, n_reads, total_genes, world),
         "e2e": {"value": n_reads / (ms_e2e * 1e-3), "unit": "reads/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-        "gpu_launches": int(launches) * args.steps,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "note": "same timed loop as `value`; value excludes only the device time of the H2D copy of the read "
+                        "set (%.1f ms per step, CUDA events)" % (upload_ms / args.steps)},
+        "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
         "kernels_ms_per_step": kern,
-        "bv_scan": {"pairs": st["bv_pairs"], "ms": st["bv_ms"], "alg_gbs": bv_gbs, "alg_frac_of_hbm": bv_gbs / hbm},
+        "bv_scan": {"pairs": st["bv_pairs"], "ms": st["bv_ms"], "alg_gbs": bv_gbs, "alg_frac_of_hbm": bv_gbs / hbm,
+                    "note": "tiled regime (seeds resident in shared memory): algorithmic bytes, not DRAM traffic; the "
+                            "streaming regime is measured by tools/bv_stream_bench.py (profiles/)"},
         "library_ms": {"cluster_reads": st["total_ms"], "correct_reads": st2["total_ms"] if st2 else 0.0,
-                       "poa_wall": st2["poa_wall_ms"] if st2 else 0.0},
+                       "poa_wall": st2["poa_wall_ms"] if st2 else 0.0, "upload": st["upload_ms"]},
         "counters": {"clusters": int(cl.n_clusters), "waves": st["waves"], "rounds": st["rounds"],
                      "full_pairs": st["full_pairs"], "heavy_pairs": st["heavy_pairs"],
-                     "poa_cells": st2["poa_cells"] if st2 else 0, "poa_alignments": st2["poa_alignments"] if st2 else 0},
+                     "poa_cells": st2["poa_cells"] if st2 else 0, "poa_alignments": st2["poa_alignments"] if st2 else 0,
+                     **digests},
     }
     # ---- CPU baseline on a bounded sample (rank 0, N=1)
     if world == 1 and not args.no_cpu_baseline:
         try:
             import oracle
             cores = os.cpu_count() or 1
-            srs = make_workload(args.ref_genes)
+            genes = ref_sample_genes(args)
+            srs = make_workload(genes)
             if oracle.have_ref():
                 lib, kind = oracle.reference(), "reference"
             else:
@@ -345,8 +447,9 @@ def main():
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": srs.n / dt, "unit": "reads/s", "cores": cores, "kind": kind,
                                     "sample": "same generator at %d genes x 50 = %d reads, cluster%s, %d threads, %.1f s "
-                                              "(clustering cost grows ~quadratically: the 100 k-read rate is lower)" % (
-                                                  args.ref_genes, srs.n, "+correct" if args.correct else "", cores, dt)}
+                                              "(clustering cost grows ~quadratically: the full-size rate is lower)" % (
+                                                  genes, srs.n, "+correct" if args.correct else "", cores, dt),
+                                    "full_config_one_off": full_config_reference()}
         except Exception as e:  # the baseline is reporting only
             line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 0, "kind": "port", "sample": "failed: %s" % e}
     print(json.dumps(line))

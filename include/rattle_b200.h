@@ -84,6 +84,10 @@ typedef struct {
                                 poa_ms, the sum of their device times, can exceed it) */
     double poa_busy_ms;      /* device time with at least one POA launch group running (union of the groups'
                                 CUDA-event intervals): the denominator of the POA roofline */
+    double upload_ms;        /* device time of the H2D copy of the read set (CUDA events around it, rtl_cluster_reads /
+                                rtl_reads_upload): lets a caller separate the resident part of an end-to-end call */
+    int64_t poa_dram_bytes;  /* bytes the POA DP kernels wrote to HBM by construction: traceback codes
+                                (rows x strips x 512 B) + spilled score rows + pass hand-over words */
 } rtl_stats;
 int rtl_get_stats(const rtl_ctx *ctx, rtl_stats *out);
 

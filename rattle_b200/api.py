@@ -27,7 +27,7 @@ class Stats(ctypes.Structure):
                 ("heavy_pairs", c_i64), ("join_ms", c_d), ("heavy_ms", c_d), ("extract_ms", c_d), ("waves", c_i64),
                 ("rounds", c_i64), ("kernel_launches", c_i64), ("h2d_bytes", c_i64), ("d2h_bytes", c_i64),
                 ("poa_alignments", c_i64), ("poa_cells", c_i64), ("poa_ms", c_d), ("poa_launches", c_i64),
-                ("total_ms", c_d), ("poa_wall_ms", c_d), ("poa_busy_ms", c_d)]
+                ("total_ms", c_d), ("poa_wall_ms", c_d), ("poa_busy_ms", c_d), ("upload_ms", c_d), ("poa_dram_bytes", c_i64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

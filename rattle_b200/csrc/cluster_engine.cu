@@ -82,6 +82,7 @@ struct ClusterState {
     PinBuf<int> h_flags;
     PinBuf<unsigned long long> h_counters;
     EvPool ev;
+    EventTimer up_timer;
     bool smem_attr_set = false;
 };
 
@@ -115,12 +116,19 @@ void cluster_upload(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, ui
     for (uint32_t i = 0; i <= n; ++i) S.h_off[i] = offsets[i] - o0;
     S.h_len.resize(n);
     for (uint32_t i = 0; i < n; ++i) S.h_len[i] = (int32_t)(S.h_off[i + 1] - S.h_off[i]);
-    CK(cudaMemcpyAsync(S.d_bases.need(S.total + 16), bases + o0, S.total, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(S.d_off.need(n + 1), S.h_off.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
-                       ctx->stream));
+    S.d_bases.need(S.total + 16);
+    S.d_off.need(n + 1);
+    S.up_timer.init();
+    CK(cudaEventRecord(S.up_timer.a, ctx->stream));
+    CK(cudaMemcpyAsync(S.d_bases.p, bases + o0, S.total, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(S.d_off.p, S.h_off.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(S.up_timer.b, ctx->stream));
     ctx->stats.h2d_bytes += (int64_t)S.total + (int64_t)(n + 1) * 8;
     S.ex_k = -1;
     CK(cudaStreamSynchronize(ctx->stream));
+    float up_ms = 0;
+    CK(cudaEventElapsedTime(&up_ms, S.up_timer.a, S.up_timer.b));
+    ctx->stats.upload_ms += up_ms;
 }
 
 // ------------------------------------------------------------------------------------------------ extraction

@@ -156,12 +156,11 @@ class WorkerPool {
         }
         cv_.notify_all();
         job.run_some();
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            jobs_.erase(std::find(jobs_.begin(), jobs_.end(), &job));
-        }
-        // workers that took the job before it left the list are still inside run_some()
-        while (job.done.load() < job.n || job.workers.load() != 0) std::this_thread::yield();
+        // workers that took the job are still inside run_some(): sleep until the last one reports (no spinning — the
+        // cores are needed by the other units' host phases and, with several ranks per node, by the other ranks)
+        std::unique_lock<std::mutex> lk(mu_);
+        jobs_.erase(std::find(jobs_.begin(), jobs_.end(), &job));
+        done_cv_.wait(lk, [&]() { return job.done.load() >= job.n && job.workers.load() == 0; });
     }
 
   private:
@@ -179,18 +178,19 @@ class WorkerPool {
                     break;
                 }
             if (!job) {
-                cv_.wait_for(lk, std::chrono::milliseconds(2));
+                cv_.wait(lk);  // woken by run() when a job is posted (posted under mu_: no lost wake-up)
                 continue;
             }
             job->workers.fetch_add(1);
             lk.unlock();
             job->run_some();
-            job->workers.fetch_sub(1);
             lk.lock();
+            job->workers.fetch_sub(1);  // under mu_, so that the owner's predicate check cannot miss it
+            done_cv_.notify_all();
         }
     }
     std::mutex mu_;
-    std::condition_variable cv_;
+    std::condition_variable cv_, done_cv_;
     std::vector<PoolJob *> jobs_;
 };
 }  // namespace
@@ -575,7 +575,14 @@ static void submit(rtl_ctx *ctx, PoaState &P, PoaSlot &S, std::vector<JobRef> &&
     S.pending = true;
     S.st.poa_alignments += (int64_t)nj;
     S.st.d2h_bytes += (int64_t)(aln_off[nj] * 8 + nj * 4);
-    for (size_t i = 0; i < nj; ++i) S.st.poa_cells += (int64_t)jobs[i].L * jobs[i].n;
+    for (size_t i = 0; i < nj; ++i) {
+        S.st.poa_cells += (int64_t)jobs[i].L * jobs[i].n;
+        if (jobs[i].kind == JK_STRIP)  // codes + spilled rows (H, F, halo) + pass hand-over words
+            S.st.poa_dram_bytes += (int64_t)jobs[i].code_bytes + (int64_t)(jobs[i].n_spill + 1) * jobs[i].nst * 1028 +
+                                   (jobs[i].nst > PS_MAXW ? 4 * (int64_t)jobs[i].n : 0);
+        else
+            S.st.poa_dram_bytes += (int64_t)jobs[i].code_bytes + (int64_t)jobs[i].hf_bytes;
+    }
     S.t_stage += now_ms() - ts0;
 }
 
@@ -888,6 +895,7 @@ void poa_chain(rtl_ctx *ctx, int unit, std::vector<PoaTask *> &tasks, int sm, in
         d.kernel_launches += S.st.kernel_launches;
         d.poa_alignments += S.st.poa_alignments;
         d.poa_cells += S.st.poa_cells;
+        d.poa_dram_bytes += S.st.poa_dram_bytes;
         d.poa_ms += S.st.poa_ms;
         if (getenv("RTL_TRACE"))
             fprintf(stderr, "[rtl] poa_chain unit %d: %zu tasks, %.1f ms (waited for GPU %.1f, fold %.1f, stage+submit %.1f), "
