@@ -220,4 +220,24 @@ int ref_correct_reads(const char *bases, const char *quals, const uint64_t *offs
     return rc;
 }
 
+// fix_msa_ends (correct.cpp:32) on caller buffers: rows = n x ncol chars (edited in place); read i's bases / qualities
+// at off[i]..off[i+1] (edited in place, new_len[i] = what is left of them)
+int ref_fix_msa_ends(char *rows, int n, int ncol, char *seqs, char *quals, const int64_t *off, int32_t *new_len) {
+    read_set_t reads(n);
+    msa_t aln(n);
+    for (int i = 0; i < n; ++i) {
+        reads[i].seq.assign(seqs + off[i], seqs + off[i + 1]);
+        reads[i].quality.assign(quals + off[i], quals + off[i + 1]);
+        aln[i].assign(rows + (size_t)i * ncol, ncol);
+    }
+    fix_msa_ends(reads, aln);
+    for (int i = 0; i < n; ++i) {
+        memcpy(rows + (size_t)i * ncol, aln[i].data(), ncol);
+        new_len[i] = (int32_t)reads[i].seq.size();
+        memcpy(seqs + off[i], reads[i].seq.data(), reads[i].seq.size());
+        memcpy(quals + off[i], reads[i].quality.data(), reads[i].quality.size());
+    }
+    return 0;
+}
+
 }  // extern "C"

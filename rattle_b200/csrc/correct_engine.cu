@@ -11,12 +11,9 @@
 
 #include "common.cuh"
 #include "poa_engine.hpp"
+#include "msa_ends.hpp"
 
 namespace {
-
-struct Read {
-    std::string header, seq, ann, quality;
-};
 
 // utils.cpp:6-13
 inline char phred_symbol(double p) { return (char)(-10 * log10(p) + 33); }
@@ -53,54 +50,6 @@ std::string reverse_complement(const std::string &s) {
         r[i] = o;
     }
     return r;
-}
-
-// correct.cpp:32-92, literally (including the case where a fully blanked row is left reversed)
-void fix_msa_ends(std::vector<Read> &reads, std::vector<std::string> &aln) {
-    for (size_t i = 0; i < aln.size(); ++i) {
-        bool reversed = false;
-        std::string &row = aln[i];
-    remove_blocks:
-        int pos = 0, end_pos = 0;
-        const int n = (int)row.size();
-        while (pos < n) {
-            while (pos < n && row[pos] == '-') ++pos;
-            end_pos = pos;
-            int gaps = 0, sz = 0;
-            while (gaps < 4 && end_pos < n) {
-                if (row[end_pos] == '-') ++gaps;
-                else {
-                    ++sz;
-                    gaps = 0;
-                }
-                ++end_pos;
-            }
-            bool flip = true;
-            if (sz < 10) {
-                while (end_pos < n && row[end_pos] == '-') {
-                    ++end_pos;
-                    ++gaps;
-                }
-                if (gaps >= 20) {
-                    for (int j = pos; j < end_pos; ++j) row[j] = '-';
-                    reads[i].quality.erase(0, sz);
-                    reads[i].seq.erase(0, sz);
-                    pos = end_pos;
-                    flip = false;
-                }
-            }
-            if (flip) {
-                std::reverse(row.begin(), row.end());
-                std::reverse(reads[i].quality.begin(), reads[i].quality.end());
-                std::reverse(reads[i].seq.begin(), reads[i].seq.end());
-                if (!reversed) {
-                    reversed = true;
-                    goto remove_blocks;
-                }
-                break;
-            }
-        }
-    }
 }
 
 // Column statistics of generate_consensus_vector (correct.cpp:94-193).  Symbols are indexed in the iteration order
@@ -424,8 +373,7 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
             parallel_for(nt, mine.size(), [&](size_t i) {
                 Pack &p = *mine[i];
                 std::vector<std::string> msa;
-                p.t1.g.msa(msa);
-                p.t1.g.clear();
+                p.t1.take_msa(msa);
                 fix_msa_ends(p.creads, msa);
                 correct_pack(p.creads, msa, min_occ, gap_occ, 30.0, p.corrected, p.uncorrected);
                 append_fastq(p.fq_corrected, p.corrected);
@@ -445,8 +393,7 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
             parallel_for(nt, mine.size(), [&](size_t i) {
                 Pack &p = *mine[i];
                 std::vector<std::string> msa;
-                p.t2.g.msa(msa);
-                p.t2.g.clear();
+                p.t2.take_msa(msa);
                 fix_msa_ends(p.sorted_corrected, msa);
                 ColStats cs;
                 consensus_vector(p.sorted_corrected, msa, cs);
@@ -524,7 +471,7 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
             labels_result;
         if (it.size() > 1) {
             std::vector<std::string> msa;
-            t3[cid].g.msa(msa);
+            t3[cid].take_msa(msa);
             fix_msa_ends(it, msa);
             ColStats cs;
             consensus_vector(it, msa, cs);

@@ -29,14 +29,15 @@ constexpr uint32_t DG_FAR = 0x80000000u;  // = PS_FAR (poa_strip_kernel.cuh)
 struct DGView {
     int32_t *in_head, *in_tail, *al_head, *al_tail, *order, *rank, *slot, *e_begin, *e_next_in, *a_node, *a_next, *stack,
         *pending;
-    uint8_t *letter, *mark, *check, *spillf;
+    uint32_t *nrec;  // compact node records of the device-resident chains (poa_devchain.cuh), 2 words per node
+    uint8_t *letter, *mark, *check, *lead, *spillf;  // lead[r] = 1: rank r opens an aligned group (an MSA column)
 };
 
 // int32 words of one graph's block for the given capacities
 DG_HD size_t dg_words(int cap_n, int cap_e, int cap_a) {
     const size_t w = (size_t)cap_n * 6 + (size_t)(cap_n + 1) + (size_t)cap_e * 2 + (size_t)cap_a * 2 + (size_t)(2 * cap_n + 2) +
-                     (size_t)(cap_e + cap_a + 2);
-    const size_t bytes = (size_t)cap_n * 3 + (size_t)(cap_n + 1);
+                     (size_t)(cap_e + cap_a + 2) + (size_t)cap_n * 2 + 1;
+    const size_t bytes = (size_t)cap_n * 4 + (size_t)(cap_n + 1);
     return ((w + (bytes + 3) / 4) + 3) & ~(size_t)3;
 }
 
@@ -55,10 +56,13 @@ DG_HD DGView dg_view(int32_t *b, int cap_n, int cap_e, int cap_a) {
     v.a_next = b; b += cap_a;
     v.stack = b; b += 2 * cap_n + 2;
     v.pending = b; b += cap_e + cap_a + 2;
+    if (reinterpret_cast<uintptr_t>(b) & 4) ++b;  // records are read as 8-byte words
+    v.nrec = reinterpret_cast<uint32_t *>(b); b += 2 * cap_n;
     uint8_t *c = reinterpret_cast<uint8_t *>(b);
     v.letter = c; c += cap_n;
     v.mark = c; c += cap_n;
     v.check = c; c += cap_n;
+    v.lead = c; c += cap_n;
     v.spillf = c;
     return v;
 }
@@ -145,8 +149,12 @@ DG_HD void dg_toposort(DGView &g, int n) {
                 }
                 g.mark[fv] = 2;
                 if (g.check[fv]) {
+                    g.lead[emitted] = 1;
                     g.order[emitted++] = fv;
-                    for (int x = g.al_head[fv]; x >= 0; x = g.a_next[x]) g.order[emitted++] = g.a_node[x];
+                    for (int x = g.al_head[fv]; x >= 0; x = g.a_next[x]) {
+                        g.lead[emitted] = 0;
+                        g.order[emitted++] = g.a_node[x];
+                    }
                 }
                 sp -= 2;
             }
@@ -208,8 +216,10 @@ DG_HD void dg_plan_spills(DGView &g, int n, int K, int32_t *counters, int32_t *s
 }
 // step 3c (all lanes): row records (layout: poa_strip_kernel.cuh); rows with more than 3 predecessors claim room in
 // `preds` (counters[1] = words used).  rec[0] and spill_rows[0] describe the virtual start row.
-DG_HD void dg_build_recs(DGView &g, int n, int K, int32_t *counters, uint32_t *rec /* 4 words per row */, int32_t *preds,
-                         int32_t *spill_rows, int lane, int nl) {
+// Returns the largest in-degree this lane met (the strip kernel's codes hold 5-bit predecessor indices).
+DG_HD int dg_build_recs(DGView &g, int n, int K, int32_t *counters, uint32_t *rec /* 4 words per row */, int32_t *preds,
+                        int32_t *spill_rows, int lane, int nl) {
+    int max_np = 0;
     if (lane == 0) {
         rec[0] = rec[1] = rec[2] = rec[3] = 0u;
         spill_rows[0] = 0;
@@ -218,6 +228,7 @@ DG_HD void dg_build_recs(DGView &g, int n, int K, int32_t *counters, uint32_t *r
         const int v = g.order[r - 1];
         int np = 0;
         for (int x = g.in_head[v]; x >= 0; x = g.e_next_in[x]) ++np;
+        if (np > max_np) max_np = np;
         uint32_t w[4] = {0u, 0u, 0u, 0u};
         if (np == 0) {  // no in-edge: the virtual start row (row 0 = spill slot 0 unless within the ring)
             w[1] = (r <= K) ? (uint32_t)r : DG_FAR;
@@ -246,6 +257,7 @@ DG_HD void dg_build_recs(DGView &g, int n, int K, int32_t *counters, uint32_t *r
         rec[4 * r + 2] = w[2];
         rec[4 * r + 3] = w[3];
     }
+    return max_np;
 }
 
 // One graph of one step: where its mirror lives, what is new, where its row records go.

@@ -19,6 +19,7 @@
 #include "poa_kernels.cuh"
 #include "poa_strip_kernel.cuh"
 #include "poa_devgraph.cuh"
+#include "poa_devchain.cuh"
 
 using namespace rtl;
 
@@ -79,6 +80,22 @@ struct PoaSlot {
     int n_threads = 1;                                  // host threads of the unit driving this slot
     double t_wait = 0, t_fold = 0, t_stage = 0;         // RTL_TRACE phase timers of the running chain
     rtl_stats st{};                                     // counters of the running chain (merged under stats_mu)
+    // device-resident chains (poa_devchain.cuh): per-pack descriptors, sequence table, fixed per-pack slots
+    DevBuf<DCPack> c_packs;
+    PinBuf<DCPack> ch_packs;
+    DevBuf<DCSeq> c_seqs;
+    PinBuf<DCSeq> ch_seqs;
+    DevBuf<uint8_t> c_q;
+    PinBuf<uint8_t> ch_q;
+    DevBuf<int32_t> c_pool, c_preds, c_spill, c_aln, c_path, c_qnode, c_list;
+    DevBuf<uint4> c_rec;
+    DevBuf<unsigned int> c_counter;
+    DevBuf<unsigned long long> c_stats;
+    PinBuf<unsigned long long> ch_stats;
+    DevBuf<uint64_t> c_msa_off;
+    PinBuf<uint64_t> ch_msa_off;
+    DevBuf<char> c_msa;
+    PinBuf<char> ch_msa;
 };
 
 constexpr int POA_MAX_UNITS = 16;
@@ -253,6 +270,7 @@ static PoaState &pstate(rtl_ctx *ctx) {
         }
         CK(cudaFuncSetAttribute(k_poa_strip<5, -4, -8, -6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)ps_smem_bytes(PS_MAXW, PS_K)));
+        CK(cudaFuncSetAttribute(k_poa_chain<5, -4, -8, -6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         P.n_threads = host_threads();
         if (const char *tf = getenv("RTL_TRACE_FILE")) P.trace = fopen(tf, "w");
         CK(cudaEventCreate(&P.ev_ref));
@@ -738,8 +756,263 @@ static void run_fold(rtl_ctx *ctx, PoaSlot &S, std::vector<JobRef> &all, const s
     S.st.d2h_bytes += (int64_t)(2 * nm * 4);
 }
 
-// One unit's chain: its tasks advance in lock-step on slot `unit`, synchronously (the calling thread is the unit's
-// driver).  n_threads = host threads this chain may use for folding/staging.
+// ------------------------------------------------------------------------------------------------ device-resident chains
+// Whole per-pack chains on the GPU (poa_devchain.cuh): the host lays out fixed per-pack slots from what it knows in
+// advance (read lengths -> capacities, strips, CTA width), uploads the packs' reads once and launches k_poa_chain once
+// per CTA width — one CTA works through a pack's whole chain.  It synchronises twice at the end (MSA sizes, MSA rows).
+// Packs the device flags (capacity, in-degree > 32, spill slots) are returned in `failed` for the host-driven path.
+
+struct ChainPlanSeg {
+    size_t begin, end;  // range of the launch list
+    int key;            // warps per CTA
+};
+
+struct ChainSizes {
+    int cap_n, cap_e, cap_a, spill_cap, max_nst, maxlen;
+    long long total;
+    size_t hf_words, code_words, arena_bytes;
+};
+
+static ChainSizes chain_sizes(const rtl_ctx *ctx, const PoaTask *t) {
+    ChainSizes z{};
+    for (int l : t->len) {
+        z.maxlen = std::max(z.maxlen, l);
+        z.total += l;
+    }
+    const long long cn = std::max<long long>(16, std::min<long long>(z.total + 8, 4ll * z.maxlen + 1024) * ctx->poa_mirror_pct / 100);
+    z.cap_n = (int)cn;
+    z.cap_e = (int)(3 * cn);
+    z.cap_a = (int)(4 * cn);
+    z.spill_cap = (int)std::min<long long>(65000, cn / 8 + 16);
+    z.max_nst = (z.maxlen + PS_STRIP - 1) / PS_STRIP;
+    z.hf_words = (ps_hf_words(z.cap_n, z.max_nst, z.spill_cap) + 63) & ~(size_t)63;
+    z.code_words = (ps_code_words(z.cap_n, z.max_nst) + 63) & ~(size_t)63;
+    z.arena_bytes = (z.hf_words + z.code_words) * 4;
+    return z;
+}
+
+static void dev_chain_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vector<PoaTask *> &batch,
+                            const std::vector<ChainSizes> &sizes, std::vector<PoaTask *> &failed) {
+    const double ts0 = now_ms();
+    cudaStream_t st = S.stream;
+    const size_t np = batch.size();
+    const uint8_t *tab = letter_codes();
+    // ---- per-pack slots
+    size_t n_seq_total = 0, q_bytes = 0, pool_words = 0, rec_rows = 0, pred_words = 0, spill_words = 0, aln_pairs = 0,
+           path_words = 0, qnode_words = 0, arena_words = 0;
+    DCPack *hp = S.ch_packs.need_geo(np);
+    for (size_t i = 0; i < np; ++i) {
+        const PoaTask *t = batch[i];
+        const ChainSizes &z = sizes[i];
+        DCPack &K = hp[i];
+        memset(&K, 0, sizeof(K));
+        K.gbase = pool_words;
+        K.hf_off = arena_words;
+        K.code_off = arena_words + z.hf_words;
+        K.rec_off = (uint32_t)rec_rows;
+        K.pred_base = (uint32_t)pred_words;
+        K.spill_off = (uint32_t)spill_words;
+        K.aln_off = (uint32_t)aln_pairs;
+        K.path_off = (uint32_t)path_words;
+        K.qnode_off = (uint32_t)qnode_words;
+        K.seq_base = (uint32_t)n_seq_total;
+        K.n_seq = (int32_t)t->seq.size();
+        K.cap_n = z.cap_n;
+        K.cap_e = z.cap_e;
+        K.cap_a = z.cap_a;
+        K.spill_cap = z.spill_cap;
+        pool_words += dg_words(z.cap_n, z.cap_e, z.cap_a);
+        arena_words += z.hf_words + z.code_words;
+        rec_rows += (size_t)z.cap_n + 1;
+        pred_words += (size_t)z.cap_e + 4;
+        spill_words += (size_t)z.cap_n + 4;
+        aln_pairs += (size_t)z.cap_n + z.maxlen + 8;
+        path_words += (size_t)z.total;
+        qnode_words += (size_t)z.maxlen + 8;
+        n_seq_total += t->seq.size();
+        for (int l : t->len) q_bytes += (size_t)((l + PS_STRIP - 1) / PS_STRIP) * PS_STRIP;
+    }
+    if (arena_words * 4 > S.arena_bytes) throw StateError("device-chain batch exceeds the unit's arena");
+    if (rec_rows >= (1ull << 31) || pred_words >= (1ull << 31) || aln_pairs >= (1ull << 30) || path_words >= (1ull << 31) ||
+        q_bytes >= (1ull << 32))
+        throw CapacityError("device-chain batch too large for 32-bit offsets");
+    // ---- sequence table and query codes
+    DCSeq *hs = S.ch_seqs.need_geo(n_seq_total);
+    uint8_t *hq = S.ch_q.need_geo(q_bytes + 16);
+    {
+        std::vector<size_t> qo(np + 1, 0);
+        for (size_t i = 0; i < np; ++i) {
+            size_t b = 0;
+            for (int l : batch[i]->len) b += (size_t)((l + PS_STRIP - 1) / PS_STRIP) * PS_STRIP;
+            qo[i + 1] = qo[i] + b;
+        }
+        parallel_for(S.n_threads, np, [&](size_t i) {
+            const PoaTask *t = batch[i];
+            size_t at = qo[i];
+            uint32_t prel = 0;
+            for (size_t s = 0; s < t->seq.size(); ++s) {
+                const int L = t->len[s], nst = (L + PS_STRIP - 1) / PS_STRIP;
+                DCSeq &Q = hs[hp[i].seq_base + s];
+                Q.q_off = (uint32_t)at;
+                Q.path_rel = prel;
+                Q.L = L;
+                Q.pad = 0;
+                const char *src = t->seq[s];
+                for (int x = 0; x < L; ++x) hq[at + x] = tab[(unsigned char)src[x]];
+                memset(hq + at + L, 255, (size_t)nst * PS_STRIP - L);
+                at += (size_t)nst * PS_STRIP;
+                prel += (uint32_t)L;
+            }
+        });
+    }
+    // ---- launch plan: one k_poa_chain launch per CTA width (warps = strips of the pack's longest read, balanced over
+    // passes beyond 8 strips); inside a launch the packs with the most DP work are fetched first
+    struct Ent {
+        int key;
+        double work;
+        int32_t pack;
+    };
+    std::vector<Ent> ents(np);
+    for (size_t i = 0; i < np; ++i) {
+        double w = 0, sum = 0;
+        for (int l : batch[i]->len) {
+            w += (double)l * sum;  // read x (nodes so far, at most the bases so far)
+            sum += l;
+        }
+        ents[i] = Ent{strip_warps(sizes[i].max_nst), w, (int32_t)i};
+    }
+    std::sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) {
+        if (a.key != b.key) return a.key > b.key;
+        if (a.work != b.work) return a.work > b.work;
+        return a.pack < b.pack;
+    });
+    std::vector<ChainPlanSeg> segs;
+    std::vector<int32_t> list(np);
+    for (size_t i = 0; i < np; ++i) {
+        list[i] = ents[i].pack;
+        if (segs.empty() || segs.back().key != ents[i].key) segs.push_back(ChainPlanSeg{i, i, ents[i].key});
+        segs.back().end = i + 1;
+    }
+    const size_t n_segs = segs.size();
+    // ---- device buffers + upload
+    S.c_pool.need_geo(pool_words);
+    S.c_rec.need_geo(rec_rows + 1);
+    S.c_preds.need_geo(pred_words + 1);
+    S.c_spill.need_geo(spill_words + 1);
+    S.c_aln.need_geo(2 * aln_pairs + 2);
+    S.c_path.need_geo(path_words + 1);
+    S.c_qnode.need_geo(qnode_words + 1);
+    S.c_counter.need_geo(n_segs + 1);
+    S.c_stats.need_geo(8);
+    CK(cudaMemcpyAsync(S.c_packs.need_geo(np), hp, np * sizeof(DCPack), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(S.c_seqs.need_geo(n_seq_total), hs, n_seq_total * sizeof(DCSeq), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(S.c_q.need_geo(q_bytes + 16), hq, q_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(S.c_list.need_geo(np), list.data(), np * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(S.c_counter.p, 0, (n_segs + 1) * sizeof(unsigned int), st));
+    CK(cudaMemsetAsync(S.c_stats.p, 0, 8 * sizeof(unsigned long long), st));
+    S.st.h2d_bytes += (int64_t)(np * sizeof(DCPack) + n_seq_total * sizeof(DCSeq) + q_bytes + np * 4);
+    // ---- the chains: one launch per CTA width, side by side on the unit's sub-streams; no host synchronisation until
+    // the MSA sizes are needed
+    CK(cudaEventRecord(S.ev0, st));
+    const bool fork = n_segs > 1 && n_segs <= (size_t)PoaSlot::N_SEG_EV;
+    if (fork) CK(cudaEventRecord(S.ev_h2d, st));
+    for (size_t si = 0; si < n_segs; ++si) {
+        const ChainPlanSeg &sg_ = segs[si];
+        cudaStream_t ss = fork ? S.sub[si % PoaSlot::N_SUB] : st;
+        if (fork) CK(cudaStreamWaitEvent(ss, S.ev_h2d, 0));
+        const int cnt = (int)(sg_.end - sg_.begin);
+        const int nw = sg_.key, K = strip_ring_rows(nw);
+        // dynamic shared memory: the DP's profiles and row ring, or — between two DPs — the working set of the graph's
+        // sort; up to 72 KB so that three CTAs still share an SM
+        const size_t smem = std::max(ps_smem_bytes(nw, K), (size_t)72 * 1024);
+        const int smem_cap_n = dc_sort_cap(smem);
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_poa_chain<5, -4, -8, -6>, nw * 32, smem));
+        const int grid = (int)std::min<size_t>((size_t)cnt, (size_t)ctx->n_sm * std::max(1, occ));
+        k_poa_chain<5, -4, -8, -6><<<grid, nw * 32, smem, ss>>>(S.c_packs.p, S.c_list.p + sg_.begin, cnt, S.c_seqs.p, S.c_pool.p,
+                                                                S.c_q.p, S.c_rec.p, S.c_preds.p, S.c_spill.p, S.c_aln.p,
+                                                                S.c_path.p, S.c_qnode.p, (uint32_t *)S.arena, S.c_stats.p,
+                                                                S.c_counter.p + si, K, smem_cap_n);
+        CK(cudaGetLastError());
+        S.st.poa_launches++;
+        S.st.kernel_launches++;
+        if (fork) {
+            CK(cudaEventRecord(S.ev_seg[si], ss));
+            CK(cudaStreamWaitEvent(st, S.ev_seg[si], 0));
+        }
+    }
+    CK(cudaEventRecord(S.ev1, st));
+    CK(cudaMemcpyAsync(hp, S.c_packs.p, np * sizeof(DCPack), cudaMemcpyDeviceToHost, st));
+    unsigned long long *hst = S.ch_stats.need(8);
+    CK(cudaMemcpyAsync(hst, S.c_stats.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    const double ts1 = now_ms();
+    S.t_stage += ts1 - ts0;
+    CK(cudaStreamSynchronize(st));
+    const double ts2 = now_ms();
+    S.t_wait += ts2 - ts1;
+    // ---- MSA rows of the packs that made it, compact
+    uint64_t *hmo = S.ch_msa_off.need_geo(np + 1);
+    size_t msa_bytes = 0;
+    for (size_t i = 0; i < np; ++i) {
+        hmo[i] = msa_bytes;
+        if (hp[i].status == DC_OK) msa_bytes += (size_t)hp[i].n_seq * (size_t)hp[i].ncol;
+    }
+    CK(cudaMemcpyAsync(S.c_msa_off.need_geo(np + 1), hmo, np * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    S.c_msa.need_geo(msa_bytes + 16);
+    k_chain_msa_rows<<<(unsigned)np, 256, 0, st>>>(S.c_packs.p, S.c_seqs.p, S.c_msa_off.p, S.c_pool.p, S.c_path.p, S.c_msa.p);
+    CK(cudaGetLastError());
+    S.st.kernel_launches++;
+    char *hm = S.ch_msa.need_geo(msa_bytes + 16);
+    if (msa_bytes) CK(cudaMemcpyAsync(hm, S.c_msa.p, msa_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    S.t_wait += now_ms() - ts2;
+    const double tf0 = now_ms();
+    parallel_for(S.n_threads, np, [&](size_t i) {
+        PoaTask *t = batch[i];
+        if (hp[i].status != DC_OK) return;
+        const int rows = hp[i].n_seq, ncol = hp[i].ncol;
+        t->msa_rows.resize(rows);
+        for (int r = 0; r < rows; ++r) t->msa_rows[r].assign(hm + hmo[i] + (size_t)r * ncol, (size_t)ncol);
+        t->have_msa = true;
+    });
+    for (size_t i = 0; i < np; ++i)
+        if (hp[i].status != DC_OK) failed.push_back(batch[i]);
+    S.t_fold += now_ms() - tf0;
+    float ms = 0, k0 = 0, k1 = 0;
+    CK(cudaEventElapsedTime(&ms, S.ev0, S.ev1));
+    cudaEventElapsedTime(&k0, P.ev_ref, S.ev0);
+    cudaEventElapsedTime(&k1, P.ev_ref, S.ev1);
+    S.st.poa_ms += ms;
+    S.st.poa_cells += (int64_t)hst[0];
+    S.st.poa_alignments += (int64_t)hst[1];
+    S.st.poa_dram_bytes += (int64_t)hst[2];
+    if (getenv("RTL_TRACE")) {
+        const double tot = (double)(hst[3] + hst[4] + hst[5]);
+        fprintf(stderr, "[rtl] device chains unit %d: %zu packs, CTA clocks: graph update %.1f %% (add_alignment %.1f, sort %.1f), "
+                "DP %.1f %%, traceback %.1f %% (%.0f ms of CTA time at 1.9 GHz)\n", (int)(&S - P.slot_store), np,
+                100.0 * hst[3] / std::max(1.0, tot), 100.0 * hst[6] / std::max(1.0, tot), 100.0 * hst[7] / std::max(1.0, tot),
+                100.0 * hst[4] / std::max(1.0, tot), 100.0 * hst[5] / std::max(1.0, tot), tot / 1.9e6);
+    }
+    S.st.d2h_bytes += (int64_t)(np * sizeof(DCPack) + 32 + msa_bytes);
+    S.st.h2d_bytes += (int64_t)(np * sizeof(uint64_t));
+    {
+        std::lock_guard<std::mutex> lk(P.stats_mu);
+        P.intervals.emplace_back(k0, k1);
+        if (P.trace) {
+            fprintf(P.trace, "{\"unit\": %d, \"epoch\": %d, \"jobs\": %zu, \"stage0\": %.3f, \"stage1\": %.3f, \"k0\": %.3f, \"k1\": %.3f, "
+                    "\"sync\": %.3f, \"fold\": %.3f, \"device_chain\": 1}\n", (int)(&S - P.slot_store), S.epoch, np, ts0 - P.t_ref,
+                    ts1 - P.t_ref, k0, k1, ts2 - P.t_ref, now_ms() - P.t_ref);
+            fflush(P.trace);
+        }
+    }
+}
+
+static void poa_chain_host(rtl_ctx *ctx, PoaState &P, PoaSlot &S, int unit, std::vector<PoaTask *> &tasks, int sm, int sn,
+                           int sg, int se, bool keep_alns);
+
+// One unit's chain on slot `unit`, synchronously (the calling thread is the unit's driver).  Packs that qualify run
+// wholly on the GPU (device-resident chains), in batches that fit the unit's arena slice; the others — and the packs
+// the device flags — take the host-driven lock-step path.  n_threads = host threads this chain may use.
 void poa_chain(rtl_ctx *ctx, int unit, std::vector<PoaTask *> &tasks, int sm, int sn, int sg, int se, bool keep_alns,
                int n_threads) {
     PoaState &P = pstate(ctx);
@@ -751,11 +1024,13 @@ void poa_chain(rtl_ctx *ctx, int unit, std::vector<PoaTask *> &tasks, int sm, in
     S.st = rtl_stats{};
     S.epoch++;
     const double t_begin = now_ms();
-    size_t max_steps = 0;
     const uint8_t *tab = letter_codes();
-    for (auto *t : tasks) {
-        max_steps = std::max(max_steps, t->seq.size());
+    const int maxabs = std::max(std::max(std::abs(sm), std::abs(sn)), std::max(std::abs(sg), std::abs(se)));
+    parallel_for(S.n_threads, tasks.size(), [&](size_t i) {
+        PoaTask *t = tasks[i];
         t->g.clear();
+        t->have_msa = false;
+        t->msa_rows.clear();
         if (keep_alns) t->alns.assign(t->seq.size(), {});
         bool ok = true;
         for (size_t s = 0; s < t->seq.size() && ok; ++s)
@@ -765,7 +1040,73 @@ void poa_chain(rtl_ctx *ctx, int unit, std::vector<PoaTask *> &tasks, int sm, in
                     break;
                 }
         t->acgtu = ok;
+    });
+    std::vector<PoaTask *> rest;
+    size_t n_dev = 0, n_failed = 0;
+    const bool dev_ok = ctx->poa_device_chain != 0 && ctx->poa_gpu_sort != 0 && ctx->poa_kernel != 1 && !keep_alns && sm == 5 &&
+                        sn == -4 && sg == -8 && se == -6;
+    if (dev_ok) {
+        std::vector<PoaTask *> batch;
+        std::vector<ChainSizes> sizes;
+        size_t used = 0;
+        auto flush = [&]() {
+            if (batch.empty()) return;
+            n_dev += batch.size();
+            const size_t before = rest.size();
+            dev_chain_batch(ctx, P, S, batch, sizes, rest);
+            n_failed += rest.size() - before;
+            batch.clear();
+            sizes.clear();
+            used = 0;
+        };
+        for (PoaTask *t : tasks) {
+            bool ok = t->acgtu && !t->seq.empty();
+            for (int l : t->len)
+                if (l < 1 || (int64_t)maxabs * (l + 16) >= 32000) ok = false;
+            if (!ok) {
+                rest.push_back(t);
+                continue;
+            }
+            const ChainSizes z = chain_sizes(ctx, t);
+            if (z.arena_bytes > S.arena_bytes) {
+                rest.push_back(t);
+                continue;
+            }
+            if (used + z.arena_bytes > S.arena_bytes) flush();
+            batch.push_back(t);
+            sizes.push_back(z);
+            used += z.arena_bytes;
+        }
+        flush();
+    } else {
+        rest = tasks;
     }
+    if (!rest.empty()) poa_chain_host(ctx, P, S, unit, rest, sm, sn, sg, se, keep_alns);
+    {
+        std::lock_guard<std::mutex> lk(P.stats_mu);
+        rtl_stats &d = ctx->stats;
+        d.h2d_bytes += S.st.h2d_bytes;
+        d.d2h_bytes += S.st.d2h_bytes;
+        d.poa_launches += S.st.poa_launches;
+        d.kernel_launches += S.st.kernel_launches;
+        d.poa_alignments += S.st.poa_alignments;
+        d.poa_cells += S.st.poa_cells;
+        d.poa_dram_bytes += S.st.poa_dram_bytes;
+        d.poa_ms += S.st.poa_ms;
+        if (getenv("RTL_TRACE"))
+            fprintf(stderr, "[rtl] poa_chain unit %d: %zu tasks (%zu on the device chain, %zu of them sent back, %zu host-driven), "
+                    "%.1f ms (waited for GPU %.1f, host fold/MSA %.1f, stage+submit %.1f), %d host threads\n", unit, tasks.size(),
+                    n_dev, n_failed, rest.size(), now_ms() - t_begin, S.t_wait, S.t_fold, S.t_stage, S.n_threads);
+    }
+}
+
+// Host-driven lock-step chain of one unit (the first-generation path, and the fallback of the device-resident chains):
+// every step synchronises with the host, which runs Graph::add_alignment and stages the next step.
+static void poa_chain_host(rtl_ctx *ctx, PoaState &P, PoaSlot &S, int unit, std::vector<PoaTask *> &tasks, int sm, int sn,
+                           int sg, int se, bool keep_alns) {
+    (void)unit;
+    size_t max_steps = 0;
+    for (auto *t : tasks) max_steps = std::max(max_steps, t->seq.size());
     const int maxabs = std::max(std::max(std::abs(sm), std::abs(sn)), std::max(std::abs(sg), std::abs(se)));
     // Device mirrors (poa_devgraph.cuh) for the graphs whose every read the strip kernel can take: the GPU then sorts
     // the graph and builds the row records, the host only runs add_alignment.  Capacities are generous multiples of the
@@ -886,21 +1227,6 @@ void poa_chain(rtl_ctx *ctx, int unit, std::vector<PoaTask *> &tasks, int sm, in
             finish(ctx, P, S);
         }
     }
-    {
-        std::lock_guard<std::mutex> lk(P.stats_mu);
-        rtl_stats &d = ctx->stats;
-        d.h2d_bytes += S.st.h2d_bytes;
-        d.d2h_bytes += S.st.d2h_bytes;
-        d.poa_launches += S.st.poa_launches;
-        d.kernel_launches += S.st.kernel_launches;
-        d.poa_alignments += S.st.poa_alignments;
-        d.poa_cells += S.st.poa_cells;
-        d.poa_dram_bytes += S.st.poa_dram_bytes;
-        d.poa_ms += S.st.poa_ms;
-        if (getenv("RTL_TRACE"))
-            fprintf(stderr, "[rtl] poa_chain unit %d: %zu tasks, %.1f ms (waited for GPU %.1f, fold %.1f, stage+submit %.1f), "
-                    "%d host threads\n", unit, tasks.size(), now_ms() - t_begin, S.t_wait, S.t_fold, S.t_stage, S.n_threads);
-    }
 }
 
 // device time during which at least one POA launch group was running since the last call (union of the groups'
@@ -977,7 +1303,7 @@ int poa_msa(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, uint32_t n
     ctx->stats = rtl_stats{};
     poa_run(ctx, tasks, m, nn, g, e, aln_off != nullptr);
     std::vector<std::string> msa;
-    task.g.msa(msa);
+    task.take_msa(msa);
     *msa_cols = msa.empty() ? 0 : (int)msa[0].size();
     if ((int64_t)msa.size() * (*msa_cols) > cap) throw CapacityError("msa_out too small");
     for (size_t i = 0; i < msa.size(); ++i) memcpy(msa_out + i * (size_t)(*msa_cols), msa[i].data(), *msa_cols);

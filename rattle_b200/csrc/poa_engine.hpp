@@ -23,6 +23,17 @@ struct PoaTask {
     int cap_n = 0, cap_e = 0, cap_a = 0;
     int sync_n = 0, sync_e = 0, sync_a = 0;
     std::vector<std::vector<std::pair<int32_t, int32_t>>> alns;  // filled when keep_alns
+    // packs whose whole chain ran on the GPU (poa_devchain.cuh) come back as MSA rows; `g` then stays empty
+    std::vector<std::string> msa_rows;
+    bool have_msa = false;
+    // the multiple sequence alignment of the task (graph.cpp:390-426 without the consensus row); releases the graph
+    void take_msa(std::vector<std::string> &dst) {
+        if (have_msa) dst = std::move(msa_rows);
+        else g.msa(dst);
+        msa_rows.clear();
+        have_msa = false;
+        g.clear();
+    }
 };
 
 // Runs all tasks on the GPU (split into concurrently running units); afterwards task->g holds the final graph

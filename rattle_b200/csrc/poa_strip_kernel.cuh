@@ -216,17 +216,16 @@ __device__ __forceinline__ void ps_fold_pred(const uint32_t (&cH)[4], const uint
     }
 }
 
+// The DP of ONE alignment by the whole CTA (all threads call it; it starts and ends with block barriers).  Returns the
+// best cell (value, row, column) through *best_cell (shared memory), valid for every thread after the call.
 template <int SM, int SN, int SG, int SE>
-__global__ void __launch_bounds__(PS_MAXW * 32, 3)
-k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ qcodes,
-            const uint4 *__restrict__ rec, const int32_t *__restrict__ preds, uint32_t *arena, int4 *best_out,
-            unsigned int *job_counter, int K) {
+__device__ __forceinline__ void ps_align_job(const PoaSJob &J, const uint8_t *__restrict__ qcodes, const uint4 *__restrict__ rec,
+                                             const int32_t *__restrict__ preds, uint32_t *arena, int K, uint4 *s_dyn,
+                                             int4 *best_cell) {
     // dynamic: [warp][letter][lane] packed match/mismatch scores of the warp's strip, then [warp][PS_K][H 32 | F 32]
     // ring of recent rows, then [warp][8] ring of H left of the strip
-    PS_DYNAMIC_SHARED(uint4, s_dyn);
     __shared__ unsigned long long s_mb[PS_MAXW][PS_D];
     __shared__ int s_done[PS_MAXW];
-    __shared__ int s_job;
     __shared__ int s_best[PS_MAXW][3];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -240,14 +239,7 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
     const ps_saddr prof_s = dyn_s + (uint32_t)((wid * PS_NLET * 32 + lane) * 16);             // + letter*512
     const ps_saddr ring_s = dyn_s + (uint32_t)((NW * PS_NLET * 32 + wid * K * 64 + lane) * 16);  // + idx*1024 (F +512)
     const ps_saddr hring_s = dyn_s + (uint32_t)(NW * (PS_NLET * 32 + K * 64) * 16 + wid * 32);   // + idx*4
-
-    while (true) {
-        if (tid == 0) s_job = (int)atomicAdd(job_counter, 1u);
-        __syncthreads();
-        const int jb = s_job;
-        __syncthreads();
-        if (jb >= n_jobs) break;
-        const PoaSJob J = jobs[jb];
+    {
         const int n = J.n, nst = J.n_strips;
         uint32_t *hf = arena + J.hf_off;  // word offsets below are relative to hf (a job's region is far below 16 GB)
         const uint32_t halo_o = (uint32_t)(J.n_spill + 1) * (uint32_t)nst * 256u;
@@ -515,9 +507,29 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
                     bj = oj;
                 }
             }
-            best_out[jb] = make_int4(best, bi, bj, 0);
+            *best_cell = make_int4(best, bi, bj, 0);
         }
-        // the next iteration's barriers order s_best / s_job reuse
+        __syncthreads();  // *best_cell is visible; s_best and the mailboxes may be reused by the next job
+    }
+}
+
+template <int SM, int SN, int SG, int SE>
+__global__ void __launch_bounds__(PS_MAXW * 32, 3)
+k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ qcodes,
+            const uint4 *__restrict__ rec, const int32_t *__restrict__ preds, uint32_t *arena, int4 *best_out,
+            unsigned int *job_counter, int K) {
+    PS_DYNAMIC_SHARED(uint4, s_dyn);
+    __shared__ int s_job;
+    __shared__ int4 s_cell;
+    while (true) {
+        if (threadIdx.x == 0) s_job = (int)atomicAdd(job_counter, 1u);
+        __syncthreads();
+        const int jb = s_job;
+        __syncthreads();
+        if (jb >= n_jobs) break;
+        const PoaSJob J = jobs[jb];
+        ps_align_job<SM, SN, SG, SE>(J, qcodes, rec, preds, arena, K, s_dyn, &s_cell);
+        if (threadIdx.x == 0) best_out[jb] = s_cell;
     }
 }
 
@@ -526,24 +538,17 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
 // end-to-start; the host reverses them and maps rows to node ids.  Lane k speculatively fetches the code of cell
 // (i-k, j-k); leading lanes whose move is "diagonal to row i-k-1" are committed 32 at a time, anything else takes
 // the general single step.
-__global__ void __launch_bounds__(128) k_poa_strip_traceback(const PoaSJob *__restrict__ jobs, int n_jobs,
-                                                             const uint4 *__restrict__ rec,
-                                                             const int32_t *__restrict__ preds,
-                                                             const int32_t *__restrict__ spill_rows,
-                                                             const uint32_t *__restrict__ arena,
-                                                             const int4 *__restrict__ best_in,
-                                                             const int32_t *__restrict__ pool, int32_t *aln_out,
-                                                             int32_t *aln_len) {
+// (one warp; every lane returns the number of pairs written)
+__device__ __forceinline__ int ps_traceback_warp(const PoaSJob &J, const int4 b, const uint4 *__restrict__ rec,
+                                                 const int32_t *__restrict__ preds, const int32_t *__restrict__ spill_rows,
+                                                 const uint32_t *__restrict__ arena, const int32_t *__restrict__ pool,
+                                                 int32_t *aln_out) {
     const int lane = threadIdx.x & 31;
-    const int jb = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (jb >= n_jobs) return;
-    const PoaSJob J = jobs[jb];
     const int nst = J.n_strips;
     const uint32_t *cd = arena + J.code_off;
     const uint4 *recs = rec + J.row_off;
     const int32_t *pr = preds + J.pred_base;
     const int32_t *sp = spill_rows + J.spill_off;
-    const int4 b = best_in[jb];
     const int best = b.x;
     int32_t *out = aln_out + 2 * (size_t)J.aln_off;
     int cnt = 0;
@@ -634,7 +639,22 @@ __global__ void __launch_bounds__(128) k_poa_strip_traceback(const PoaSJob *__re
             }
         }
     }
-    if (lane == 0) aln_len[jb] = cnt;
+    return cnt;
+}
+
+__global__ void __launch_bounds__(128) k_poa_strip_traceback(const PoaSJob *__restrict__ jobs, int n_jobs,
+                                                             const uint4 *__restrict__ rec,
+                                                             const int32_t *__restrict__ preds,
+                                                             const int32_t *__restrict__ spill_rows,
+                                                             const uint32_t *__restrict__ arena,
+                                                             const int4 *__restrict__ best_in,
+                                                             const int32_t *__restrict__ pool, int32_t *aln_out,
+                                                             int32_t *aln_len) {
+    const int jb = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (jb >= n_jobs) return;
+    const PoaSJob J = jobs[jb];
+    const int cnt = ps_traceback_warp(J, best_in[jb], rec, preds, spill_rows, arena, pool, aln_out);
+    if ((threadIdx.x & 31) == 0) aln_len[jb] = cnt;
 }
 
 }  // namespace rtl

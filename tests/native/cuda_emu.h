@@ -104,6 +104,7 @@ inline unsigned __ballot_sync(unsigned, bool p) {
     return m;
 }
 inline int __ffs(unsigned x) { return x ? __builtin_ctz(x) + 1 : 0; }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
 
 // packed int16 (DPX) intrinsics and friends
 inline int16_t emu_lo(uint32_t v) { return (int16_t)(v & 0xffffu); }
@@ -132,6 +133,11 @@ inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
 }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicCAS(unsigned *p, unsigned expected, unsigned desired) {
+    __atomic_compare_exchange_n(p, &expected, desired, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return expected;  // the value found
+}
 inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 
 // shared memory: the dynamic part is one host buffer (emu::g_smem), `__shared__` statics are function statics (one CTA
