@@ -197,6 +197,12 @@ int rtl_cluster_reads(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, 
                       int32_t *mem_id, uint8_t *mem_rev, int32_t *n_clusters) {
     return guarded(ctx, [&]() {
         ctx->stats = rtl_stats{};
+        if (n_reads == 0) {  // the reference returns an empty cluster set (cluster.cpp:93-259 with no reads)
+            if (!n_clusters || !cl_off) throw InputError("null output buffers");
+            *n_clusters = 0;
+            cl_off[0] = 0;
+            return RTL_OK;
+        }
         const double t0 = now_ms();
         cluster_upload(ctx, bases, offsets, n_reads);
         cluster_run(ctx, kmer_size, t_s, t_v, bv_threshold, min_bv_threshold, bv_falloff, repr_percentile, is_rna,

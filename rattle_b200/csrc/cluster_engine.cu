@@ -12,6 +12,7 @@
 
 #include "cluster_kernels.cuh"
 #include "common.cuh"
+#include "poa_engine.hpp"  // parallel_for / host_threads (shared worker pool)
 
 using namespace rtl;
 
@@ -69,12 +70,12 @@ struct ClusterState {
     DevBuf<uint64_t> long_off, long_scratch;
     // wave state
     DevBuf<uint8_t> taken, owner_rev, is_seed;
-    DevBuf<int32_t> owner, item_read, item_rid, cand, seed_item, wave;
+    DevBuf<int32_t> owner, item_read, item_rid, cand, seed_item, wave, shard_list;
     DevBuf<uint32_t> memo;      // known k-mer-test failures between representatives (cluster_kernels.cuh: Memo)
     uint32_t rid_dim = 0;       // 0 = memo off
     DevBuf<uint32_t> best, acc;
     DevBuf<uint16_t> cut;
-    DevBuf<uint64_t> tasks, surv;
+    DevBuf<uint64_t> tasks, surv, defer[2];
     DevBuf<unsigned long long> counters;  // [0]=n_tasks [1]=n_surv [2]=scratch_cur [3]=pairs
     DevBuf<int> flags;                    // [0]=input err [1]=overflow
     DevBuf<unsigned char> scratch;
@@ -109,6 +110,12 @@ static void set_smem_attrs(ClusterState &S) {
 void cluster_upload(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, uint32_t n) {
     ClusterState &S = state(ctx);
     if (n == 0) throw InputError("empty read set");
+    if (!bases || !offsets) throw InputError("null read buffers");
+    if (n >= (1u << 31)) throw InputError("more than 2^31 reads");
+    for (uint32_t i = 0; i < n; ++i) {
+        if (offsets[i + 1] < offsets[i]) throw InputError("read offsets are not monotonic");
+        if (offsets[i + 1] - offsets[i] > 0x7fffffffull) throw InputError("read longer than 2^31 bases");
+    }
     S.n = n;
     S.total = offsets[n] - offsets[0];
     S.h_off.resize(n + 1);
@@ -274,13 +281,27 @@ static void run_pair_kernels(rtl_ctx *ctx, ClusterState &S, const TaskView &tv, 
     S.ev.end(EV_JOIN, st);
     S.ev.begin(EV_HEAVY, st);
     const size_t smem = (size_t)(PH_THREADS / 32) * heavy_bytes(PH_CAP_C, PH_CAP_C);
+    // Survivors with more than PH_CAP_C matches sort in a global scratch arena (bump allocation).  Those that find it
+    // full are deferred: two more launches follow, each with the arena empty again (they exit at once when nothing was
+    // deferred, the usual case); only what is still left after them fails the call ("raise scratch_mb").
+    const int64_t defer_cap = (int64_t)S.defer[0].cap;
+    const unsigned long long scratch_bytes = std::min<size_t>(S.scratch.cap, (size_t)ctx->scratch_mb << 20);
+    CK(cudaMemsetAsync(S.counters.p + 6, 0, 2 * sizeof(unsigned long long), st));
     k_pair_heavy<<<ctx->n_sm * 2, PH_THREADS, smem, st>>>(tv, S.tasks.p, S.surv.p, S.counters.p + 1, surv_cap, R, t_s, t_v,
                                                           PH_CAP_C, S.scratch.p, S.counters.p + 2,
-                                                          (unsigned long long)S.scratch.cap, sink, S.flags.p + 1,
-                                                          S.counters.p + 5);
+                                                          scratch_bytes, sink, S.flags.p + 1,
+                                                          S.counters.p + 5, S.defer[0].p, S.counters.p + 6, defer_cap);
     CK(cudaGetLastError());
+    for (int r = 0; r < 2; ++r) {
+        CK(cudaMemsetAsync(S.counters.p + 2, 0, sizeof(unsigned long long), st));
+        k_pair_heavy<<<ctx->n_sm * 2, PH_THREADS, smem, st>>>(
+            tv, S.tasks.p, S.defer[r].p, S.counters.p + 6 + r, defer_cap, R, t_s, t_v, PH_CAP_C, S.scratch.p, S.counters.p + 2,
+            scratch_bytes, sink, S.flags.p + 1, nullptr, r == 0 ? S.defer[1].p : nullptr,
+            S.counters.p + 7, defer_cap);
+        CK(cudaGetLastError());
+    }
     S.ev.end(EV_HEAVY, st);
-    ctx->stats.kernel_launches += 2;
+    ctx->stats.kernel_launches += 4;
 }
 
 static void ensure_work_buffers(rtl_ctx *ctx, ClusterState &S, int64_t M) {
@@ -288,7 +309,7 @@ static void ensure_work_buffers(rtl_ctx *ctx, ClusterState &S, int64_t M) {
     S.taken.need(M);
     S.owner.need(M);
     S.owner_rev.need(M);
-    S.best.need(M);
+    S.best.need(M + 1);
     S.item_read.need(M);
     S.cand.need(W);
     S.seed_item.need(W);
@@ -298,6 +319,8 @@ static void ensure_work_buffers(rtl_ctx *ctx, ClusterState &S, int64_t M) {
     S.cut.need(4097);
     S.tasks.need(ctx->task_cap);
     S.surv.need(ctx->task_cap / 4 + 1024);
+    S.defer[0].need(1 << 16);
+    S.defer[1].need(1 << 16);
     S.counters.need(8);
     S.flags.need(4);
     S.scratch.need((size_t)ctx->scratch_mb << 20);
@@ -330,6 +353,18 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
         memo.bits = S.memo.p;
         memo.rid_dim = S.rid_dim;
     }
+    // multi-GPU: this rank's targets as a compact ascending list (key = the representative's compact id in the merge
+    // rounds, so that a rank meets the pairs it has memoised again; the item index otherwise) — phase B then walks only
+    // its own share instead of filtering every item inside the scan kernel
+    std::vector<int32_t> shard;
+    if (ctx->world > 1) {
+        shard.reserve((size_t)M / ctx->world + 1);
+        const bool by_rid = h_item_rid && S.rid_dim;
+        for (int i = 0; i < M; ++i)
+            if ((by_rid ? h_item_rid[i] : i) % ctx->world == ctx->rank) shard.push_back(i);
+        CK(cudaMemcpyAsync(S.shard_list.need(shard.size() + 1), shard.data(), shard.size() * 4, cudaMemcpyHostToDevice, st));
+        ctx->stats.h2d_bytes += (int64_t)shard.size() * 4;
+    }
     std::vector<uint16_t> cut;
     make_cut_table(thr, cut);
     CK(cudaMemcpyAsync(S.cut.p, cut.data(), 4097 * 2, cudaMemcpyHostToDevice, st));
@@ -346,6 +381,7 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
     const int64_t chunk = std::max<int64_t>(1024, ctx->task_cap / (2 * (int64_t)W));
     int32_t *hw = S.h_wave.p;
     int *hf = S.h_flags.p;
+    hw[3] = -1;
     while (lo < M) {
         k_select<<<1, 1024, 0, st>>>(S.taken.p, M, W, S.cand.p, S.wave.p);
         k_mark_cand<<<4, 256, 0, st>>>(S.taken.p, S.cand.p, S.wave.p, S.owner.p, S.owner_rev.p);
@@ -399,8 +435,12 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
         }
         // ---- phase B: seeds x every later untaken item (items below the cursor are all taken)
         const int b_lo = lo;
-        for (int64_t c0 = b_lo; c0 < M; c0 += chunk) {
-            const int64_t c1 = std::min<int64_t>(M, c0 + chunk);
+        // target space: items [b_lo, M), or — sharded — the entries of this rank's list from the first one >= b_lo
+        const bool sharded = ctx->world > 1;
+        const int64_t x_lo = sharded ? (int64_t)(std::lower_bound(shard.begin(), shard.end(), b_lo) - shard.begin()) : b_lo;
+        const int64_t x_hi = sharded ? (int64_t)shard.size() : M;
+        for (int64_t c0 = x_lo; c0 < x_hi; c0 += chunk) {
+            const int64_t c1 = std::min<int64_t>(x_hi, c0 + chunk);
             CK(cudaMemsetAsync(S.counters.p, 0, 3 * sizeof(unsigned long long), st));
             BvScanArgs a{};
             a.bv_f = S.bv[0].p;
@@ -409,15 +449,16 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
             a.item_read = d_item_read;
             a.seed_item = S.seed_item.p;
             a.n_seeds_p = S.wave.p + 2;
-            a.tgt_list = nullptr;
-            a.t0 = (int32_t)c0;
-            a.t1 = (int32_t)c1;
+            a.tgt_list = sharded ? S.shard_list.p + c0 : nullptr;
+            a.t0 = sharded ? 0 : (int32_t)c0;
+            a.t1 = sharded ? (int32_t)(c1 - c0) : (int32_t)c1;
             a.taken = S.taken.p;
             a.cut = S.cut.p;
             a.both = both;
             a.order_check = 0;
             a.rank = ctx->rank;
             a.world = ctx->world;
+            a.presharded = sharded ? 1 : 0;
             a.ts_cap = BVS_TS;
             a.memo = memo;
             a.tasks = S.tasks.p;
@@ -434,26 +475,34 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
             S.ev.end(EV_BV, st);
             ctx->stats.kernel_launches++;
             ctx->stats.bv_launches++;
-            TaskView tv{S.seed_item.p, nullptr, d_item_read, memo};
+            TaskView tv{S.seed_item.p, a.tgt_list, d_item_read, memo};
             Sink sink{};
             sink.mode = 2;
             sink.best = S.best.p;
             run_pair_kernels(ctx, S, tv, t_s, t_v, sink, nullptr);
         }
         if (b_lo < M) {
-            if (ctx->world > 1 && ctx->allreduce(ctx->allreduce_user, S.best.p + b_lo, (int64_t)(M - b_lo)) != 0)
-                throw CudaError("allreduce callback failed");
+            if (ctx->world > 1) {
+                k_fold_status<<<1, 1, 0, st>>>(S.flags.p, S.best.p + M);
+                ctx->stats.kernel_launches++;
+                if (ctx->allreduce(ctx->allreduce_user, S.best.p + b_lo, (int64_t)(M - b_lo) + 1) != 0)
+                    throw CudaError("allreduce callback failed");
+                CK(cudaMemcpyAsync(hw + 3, S.best.p + M, 4, cudaMemcpyDeviceToHost, st));  // wave[3] is unused by the host
+            }
             k_apply<<<ctx->n_sm, 256, 0, st>>>(S.best.p, b_lo, M, S.seed_item.p, S.taken.p, S.owner.p, S.owner_rev.p);
             ctx->stats.kernel_launches++;
         }
-        CK(cudaMemcpyAsync(hw, S.wave.p, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hw, S.wave.p, 12, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(hf, S.flags.p, 16, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         ctx->stats.d2h_bytes += 32;
         S.ev.collect();
         ctx->stats.waves++;
+        if (ctx->world > 1 && b_lo < M && hw[3] == 0 && !hf[1])
+            throw CapacityError("another rank ran out of candidate-pair or match scratch space: raise task_cap / scratch_mb");
         if (hf[1]) {
             if (hf[1] == 3) throw CapacityError("match scratch exhausted: raise option scratch_mb");
+            if (hf[1] == 4) throw CapacityError("a read pair has 2^31 or more common k-mer matches (not representable)");
             throw CapacityError("candidate-pair buffer exhausted: raise option task_cap");
         }
         lo = hw[0];
@@ -520,7 +569,7 @@ void cluster_run(rtl_ctx *ctx, int k, double t_s, double t_v, double bv_thr, dou
             }
         for (int i = 0; i < N; ++i)
             if (owner[i] != i) cl[slot[owner[i]]].mem.push_back(Member{i, orev[i]});
-        for (auto &c : cl) c.main = pick_main(c.mem, S.h_len, repr_pct);
+        parallel_for(host_threads(), cl.size(), [&](size_t c) { cl[c].main = pick_main(cl[c].mem, S.h_len, repr_pct); });
     }
 
     double thr = bv_thr - bv_falloff;
@@ -566,7 +615,7 @@ void cluster_run(rtl_ctx *ctx, int k, double t_s, double t_v, double bv_thr, dou
                     dst.push_back(s);
                 }
             }
-        for (auto &c : next) c.main = pick_main(c.mem, S.h_len, repr_pct);
+        parallel_for(host_threads(), next.size(), [&](size_t c) { next[c].main = pick_main(next[c].mem, S.h_len, repr_pct); });
         cl.swap(next);
         if (last) break;
         thr -= bv_falloff;
@@ -620,6 +669,10 @@ void cluster_download_kmers(rtl_ctx *ctx, uint32_t *fh, int32_t *fp, uint32_t *r
 void cluster_bv_scan_dense(rtl_ctx *ctx, int k, int is_rna, const int32_t *seed_reads, int n_seeds,
                            const int32_t *target_reads, int n_targets, double thr, uint32_t *common, uint8_t *pass) {
     ClusterState &S = state(ctx);
+    for (int i = 0; i < n_seeds; ++i)
+        if (seed_reads[i] < 0 || (uint32_t)seed_reads[i] >= S.n) throw InputError("seed read index out of range");
+    for (int i = 0; i < n_targets; ++i)
+        if (target_reads[i] < 0 || (uint32_t)target_reads[i] >= S.n) throw InputError("target read index out of range");
     cluster_extract(ctx, k, !is_rna);
     set_smem_attrs(S);
     cudaStream_t st = ctx->stream;
@@ -693,6 +746,8 @@ void cluster_pair_similarity(rtl_ctx *ctx, int k, int is_rna, const int32_t *a_r
     if (n_tasks >= (1ll << 31)) throw CapacityError("too many tasks");
     std::vector<uint64_t> tasks(n_tasks);
     for (int64_t i = 0; i < n_tasks; ++i) {
+        if (a_read[i] < 0 || (uint32_t)a_read[i] >= S.n || b_read[i] < 0 || (uint32_t)b_read[i] >= S.n)
+            throw InputError("task read index out of range");
         if (strand[i] && is_rna) throw InputError("reverse-strand task on an RNA (forward-only) extraction");
         tasks[i] = make_task((uint32_t)i, strand[i], (uint32_t)i);
     }
@@ -702,6 +757,8 @@ void cluster_pair_similarity(rtl_ctx *ctx, int k, int is_rna, const int32_t *a_r
     DevBuf<uint8_t> d_acc;
     S.tasks.need(std::max<int64_t>(n_tasks, 1));
     S.surv.need(std::max<int64_t>(n_tasks, 1));
+    S.defer[0].need(1 << 16);
+    S.defer[1].need(1 << 16);
     S.counters.need(8);
     S.flags.need(4);
     S.scratch.need((size_t)ctx->scratch_mb << 20);

@@ -269,6 +269,7 @@ struct BvScanArgs {
     int both;                  // reverse strand evaluated
     int order_check;           // require seed item < target item
     int rank, world;           // target sharding
+    int presharded;            // tgt_list already holds only this rank's targets (no filtering in the kernel)
     int ts_cap;                // seeds per tile the shared memory is sized for (<= BVS_TS; fewer seeds -> more CTAs/SM)
     Memo memo;                 // known k-mer-test failures between representatives (merge rounds)
     uint64_t *tasks;
@@ -333,7 +334,9 @@ __global__ void __launch_bounds__(BVS_THREADS) k_bv_scan(BvScanArgs A) {
         p.item = A.tgt_list ? A.tgt_list[x] : p.tslot;
         // multi-GPU: targets are sharded by a key that is stable over the merge rounds (the representative's compact
         // id), so that a rank meets the pairs it has memoised again
-        if (A.world > 1 && ((A.memo.item_rid ? A.memo.item_rid[p.item] : p.item) % A.world) != A.rank) return p;
+        if (A.world > 1 && !A.presharded &&
+            ((A.memo.item_rid ? A.memo.item_rid[p.item] : p.item) % A.world) != A.rank)
+            return p;
         const bool taken = A.taken ? (A.taken[p.item] != 0) : false;
         p.rd = A.item_read ? (uint32_t)A.item_read[p.item] : (uint32_t)p.item;
         p.live = !taken;
@@ -564,7 +567,8 @@ __global__ void __launch_bounds__(PH_THREADS) k_pair_heavy(TaskView tv, const ui
                                                            ReadView R, double t_s, double t_v, int cap_c,
                                                            unsigned char *scratch, unsigned long long *scratch_cur,
                                                            unsigned long long scratch_bytes, Sink S, int *ovf,
-                                                           unsigned long long *stat_heavy) {
+                                                           unsigned long long *stat_heavy, uint64_t *defer,
+                                                           unsigned long long *n_defer, int64_t defer_cap) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *wbase = sm_raw + (size_t)warp * heavy_bytes(cap_c, cap_c);
@@ -589,7 +593,10 @@ __global__ void __launch_bounds__(PH_THREADS) k_pair_heavy(TaskView tv, const ui
         int bases = 0, nd = 0;
         double v = 0.0;
         bool fail = false;
-        if (n32 == 0xffffffffu) fail = true;
+        if (n32 >= 0x7fffffffu) {  // 2^31 or more matches (saturated at 2^32-1 by k_join_count): not representable here
+            if (lane == 0) atomicExch(ovf, 4);
+            continue;
+        }
         const int n = (int)n32;
         int n_pad = 1;
         while (n_pad < n) n_pad <<= 1;
@@ -606,7 +613,13 @@ __global__ void __launch_bounds__(PH_THREADS) k_pair_heavy(TaskView tv, const ui
             }
         }
         if (fail) {
-            if (lane == 0) atomicExch(ovf, 3);
+            // the match scratch is full: the survivor is deferred to the next launch (which starts with an empty
+            // scratch); only when there is no room to remember it does the call fail
+            if (lane == 0) {
+                const unsigned long long d = defer ? atomicAdd(n_defer, 1ull) : ~0ull;
+                if (defer && (long long)d < defer_cap) defer[d] = rec;
+                else atomicExch(ovf, 3);
+            }
             continue;
         }
         int32_t *prev = (int32_t *)(keys + n_pad);
@@ -709,7 +722,11 @@ __global__ void __launch_bounds__(PH_THREADS) k_pair_heavy(TaskView tv, const ui
                 const uint32_t t = (uint32_t)task;
                 const uint32_t s = (uint32_t)(task >> 33);
                 if (S.mode == 1) atomicMin(&S.acc[(size_t)s * S.W + t], (uint32_t)strand);
-                else if (S.mode == 2) atomicMin(&S.best[t], s * 2 + (uint32_t)strand);
+                else if (S.mode == 2) {  // best[] is indexed by item (t indexes the target list when there is one)
+                    uint32_t ai, bi;
+                    tv.items(task, ai, bi);
+                    atomicMin(&S.best[bi], s * 2 + (uint32_t)strand);
+                }
             }
         }
         __syncwarp();
@@ -824,6 +841,10 @@ __global__ void k_apply(uint32_t *best, int t0, int M, const int32_t *seed_item,
         }
     }
 }
+
+// multi-GPU: a rank-local overflow must stop EVERY rank (the others would wait in the next exchange for ever): the flag
+// travels with the decision array as one more uint32 (0 = some rank overflowed; smaller wins in the min-reduction)
+__global__ void k_fold_status(const int *flags, uint32_t *status) { *status = flags[1] ? 0u : 0xffffffffu; }
 
 __global__ void k_fill_u32(uint32_t *p, uint32_t v, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;

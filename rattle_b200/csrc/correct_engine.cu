@@ -255,6 +255,12 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
     ctx->stats = rtl_stats{};
     if (n_clusters < 1) throw InputError("empty cluster set (correct.cpp:322 reads clusters[0])");
     if (split < 1) throw InputError("split must be >= 1");
+    if (!cl_off || !mem_id || !mem_rev || !offsets || !bases || !quals) throw InputError("null input buffers");
+    if (cl_off[0] != 0) throw InputError("cl_off must start at 0");
+    for (int c = 0; c < n_clusters; ++c)
+        if (cl_off[c + 1] < cl_off[c]) throw InputError("cl_off is not monotonic");
+    for (uint32_t i = 0; i < n_reads; ++i)
+        if (offsets[i + 1] < offsets[i]) throw InputError("read offsets are not monotonic");
     const int nthreads = host_threads();
     const bool gene_mode = (main_gene ? main_gene[0] : -1) == -1;
 
@@ -370,6 +376,7 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
                 tasks.push_back(&p->t1);
             }
             poa_chain(ctx, u, tasks, 5, -4, -8, -6, false, nt);
+            const double tv0 = now_ms();
             parallel_for(nt, mine.size(), [&](size_t i) {
                 Pack &p = *mine[i];
                 std::vector<std::string> msa;
@@ -384,12 +391,14 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
                 std::vector<Read>().swap(p.corrected);
                 std::vector<Read>().swap(p.uncorrected);
             });
+            const double tv1 = now_ms();
             tasks.clear();
             for (Pack *p : mine) {
                 set_task(p->t2, p->sorted_corrected);
                 tasks.push_back(&p->t2);
             }
             poa_chain(ctx, u, tasks, 5, -4, -8, -6, false, nt);
+            const double tv2 = now_ms();
             parallel_for(nt, mine.size(), [&](size_t i) {
                 Pack &p = *mine[i];
                 std::vector<std::string> msa;
@@ -399,6 +408,9 @@ int correct_reads_impl(rtl_ctx *ctx, const char *bases, const char *quals, const
                 consensus_vector(p.sorted_corrected, msa, cs);
                 p.consensus = strip_gaps(cs.consensus);
             });
+            if (trace)
+                fprintf(stderr, "[rtl] correct unit %d: host column vote + read correction %.1f ms, consensus vote %.1f ms (%d threads)\n",
+                        u, tv1 - tv0, now_ms() - tv2, nt);
         });
         ctx->stats.poa_wall_ms += now_ms() - tp0;
         poa_account_busy(ctx);

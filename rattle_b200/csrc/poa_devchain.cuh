@@ -705,8 +705,10 @@ __device__ __forceinline__ void dc_msa_cols_warp(DCPack &P, int32_t *pool) {
 // the graph's sort in the CTA's shared memory between two DPs.  `list` = the packs of this launch (all of one CTA
 // width), largest first; CTAs fetch packs from it until it is empty.  stats: [0] DP cells, [1] alignments, [2] bytes the
 // DP writes by construction.
-template <int SM, int SN, int SG, int SE>
-__global__ void __launch_bounds__(PS_MAXW * 32, 3)
+// MAXT / MINB: launch bounds (threads per CTA, CTAs per SM) — narrower CTAs are compiled for four CTAs per SM, which
+// keeps more DP warps resident while other CTAs of the SM are in their one-warp phases (graph update, traceback).
+template <int SM, int SN, int SG, int SE, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 k_poa_chain(DCPack *packs, const int32_t *__restrict__ list, int n_list, const DCSeq *__restrict__ seqs, int32_t *pool,
             const uint8_t *__restrict__ qcodes, uint4 *rec, int32_t *preds, int32_t *spill_rows, int32_t *aln, int32_t *path,
             int32_t *qnode, uint32_t *arena, unsigned long long *stats, unsigned int *counter, int K, int smem_cap_n) {

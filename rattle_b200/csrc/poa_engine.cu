@@ -69,6 +69,8 @@ struct PoaSlot {
     cudaStream_t sub[N_SUB] = {nullptr, nullptr, nullptr, nullptr};  // segments of one group run side by side
     cudaEvent_t ev_seg[N_SEG_EV] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_h2d = nullptr, ev_dp = nullptr;
+    cudaEvent_t ev_wait = nullptr;  // blocking-sync event: a unit's driver thread SLEEPS while its kernels run (a dozen
+                                    // spinning cudaStreamSynchronize per rank would eat the cores of an 8-rank node)
     double t_submit0 = 0, t_submit1 = 0;  // host clock around the last submit (timeline trace)
     int epoch = 0;                        // chains run on this slot so far (timeline trace)
     unsigned char *arena = nullptr;  // this unit's slice of the device arena (score rows + traceback codes)
@@ -125,6 +127,7 @@ void poa_state_free(rtl_ctx *ctx) {
                 if (x) cudaEventDestroy(x);
             if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
             if (sl.ev_dp) cudaEventDestroy(sl.ev_dp);
+            if (sl.ev_wait) cudaEventDestroy(sl.ev_wait);
         }
         delete ctx->poa;
     }
@@ -242,6 +245,12 @@ int host_threads() {
     return (int)std::min(hc, 64u);
 }
 
+// wait for everything enqueued on the slot's stream without spinning
+static void slot_wait(PoaSlot &S) {
+    CK(cudaEventRecord(S.ev_wait, S.stream));
+    CK(cudaEventSynchronize(S.ev_wait));
+}
+
 static PoaState &pstate(rtl_ctx *ctx) {
     if (!ctx->poa) {
         ctx->poa = new PoaState();
@@ -263,6 +272,7 @@ static PoaState &pstate(rtl_ctx *ctx) {
             CK(cudaEventCreate(&sl.ev1));
             CK(cudaEventCreate(&sl.ev_h2d));
             CK(cudaEventCreate(&sl.ev_dp));
+            CK(cudaEventCreateWithFlags(&sl.ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
             for (auto &x : sl.sub) CK(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
             for (auto &x : sl.ev_seg) CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
             sl.arena = P.arena.p + i * part;
@@ -270,7 +280,9 @@ static PoaState &pstate(rtl_ctx *ctx) {
         }
         CK(cudaFuncSetAttribute(k_poa_strip<5, -4, -8, -6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)ps_smem_bytes(PS_MAXW, PS_K)));
-        CK(cudaFuncSetAttribute(k_poa_chain<5, -4, -8, -6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(k_poa_chain<5, -4, -8, -6, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(k_poa_chain<5, -4, -8, -6, 224, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(k_poa_chain<5, -4, -8, -6, 192, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         P.n_threads = host_threads();
         if (const char *tf = getenv("RTL_TRACE_FILE")) P.trace = fopen(tf, "w");
         CK(cudaEventCreate(&P.ev_ref));
@@ -608,7 +620,7 @@ static void submit(rtl_ctx *ctx, PoaState &P, PoaSlot &S, std::vector<JobRef> &&
 static void finish(rtl_ctx *ctx, PoaState &P, PoaSlot &S) {
     if (!S.pending) return;
     const double tw0 = now_ms();
-    CK(cudaStreamSynchronize(S.stream));
+    slot_wait(S);
     const double tw1 = now_ms();
     S.t_wait += tw1 - tw0;
     S.pending = false;
@@ -747,7 +759,7 @@ static void run_fold(rtl_ctx *ctx, PoaSlot &S, std::vector<JobRef> &all, const s
     int32_t *hc = S.h_counts.need_geo(2 * nm);
     CK(cudaMemcpyAsync(hc, S.d_counts.p, 2 * nm * 4, cudaMemcpyDeviceToHost, st));
     const double ts1 = now_ms();
-    CK(cudaStreamSynchronize(st));
+    slot_wait(S);
     S.t_wait += now_ms() - ts1;
     S.t_stage += ts1 - ts0;
     for (size_t k = 0; k < nm; ++k) all[mj[k]].n_spill = hc[2 * k];
@@ -921,18 +933,27 @@ static void dev_chain_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::ve
         cudaStream_t ss = fork ? S.sub[si % PoaSlot::N_SUB] : st;
         if (fork) CK(cudaStreamWaitEvent(ss, S.ev_h2d, 0));
         const int cnt = (int)(sg_.end - sg_.begin);
-        const int nw = sg_.key, K = strip_ring_rows(nw);
-        // dynamic shared memory: the DP's profiles and row ring, or — between two DPs — the working set of the graph's
-        // sort; up to 72 KB so that three CTAs still share an SM
-        const size_t smem = std::max(ps_smem_bytes(nw, K), (size_t)72 * 1024);
+        const int nw = sg_.key;
+        // CTAs per SM: 8-warp CTAs are register-limited to three; narrower ones run four per SM (kernel variant compiled
+        // for that), with a ring of 5 rows where that is what fits 54 KB.  Dynamic shared memory = the DP's profiles and
+        // row ring, or — between two DPs — the working set of the graph's sort.
+        const bool four = nw <= 7 && getenv("RATTLE_B200_CTAS3") == nullptr;
+        const size_t budget = four ? (size_t)54 * 1024 : (size_t)72 * 1024;
+        int K = strip_ring_rows(nw);
+        while (K > 3 && ps_smem_bytes(nw, K) > budget) --K;
+        const size_t smem = std::max(ps_smem_bytes(nw, K), budget);
         const int smem_cap_n = dc_sort_cap(smem);
+        auto kern = nw == 8 ? k_poa_chain<5, -4, -8, -6, 256, 3>
+                            : (!four ? k_poa_chain<5, -4, -8, -6, 256, 3>
+                                     : (nw == 7 ? k_poa_chain<5, -4, -8, -6, 224, 4> : k_poa_chain<5, -4, -8, -6, 192, 4>));
         int occ = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_poa_chain<5, -4, -8, -6>, nw * 32, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nw * 32, smem));
         const int grid = (int)std::min<size_t>((size_t)cnt, (size_t)ctx->n_sm * std::max(1, occ));
-        k_poa_chain<5, -4, -8, -6><<<grid, nw * 32, smem, ss>>>(S.c_packs.p, S.c_list.p + sg_.begin, cnt, S.c_seqs.p, S.c_pool.p,
-                                                                S.c_q.p, S.c_rec.p, S.c_preds.p, S.c_spill.p, S.c_aln.p,
-                                                                S.c_path.p, S.c_qnode.p, (uint32_t *)S.arena, S.c_stats.p,
-                                                                S.c_counter.p + si, K, smem_cap_n);
+        kern<<<grid, nw * 32, smem, ss>>>(S.c_packs.p, S.c_list.p + sg_.begin, cnt, S.c_seqs.p, S.c_pool.p, S.c_q.p, S.c_rec.p,
+                                          S.c_preds.p, S.c_spill.p, S.c_aln.p, S.c_path.p, S.c_qnode.p, (uint32_t *)S.arena,
+                                          S.c_stats.p, S.c_counter.p + si, K, smem_cap_n);
+        if (getenv("RTL_TRACE") && S.epoch <= 2 && (&S - P.slot_store) == 0)
+            fprintf(stderr, "[rtl] k_poa_chain: %d packs, %d warps per CTA, ring %d, %zu B smem, %d CTAs per SM\n", cnt, nw, K, smem, occ);
         CK(cudaGetLastError());
         S.st.poa_launches++;
         S.st.kernel_launches++;
@@ -947,7 +968,7 @@ static void dev_chain_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::ve
     CK(cudaMemcpyAsync(hst, S.c_stats.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     const double ts1 = now_ms();
     S.t_stage += ts1 - ts0;
-    CK(cudaStreamSynchronize(st));
+    slot_wait(S);
     const double ts2 = now_ms();
     S.t_wait += ts2 - ts1;
     // ---- MSA rows of the packs that made it, compact
@@ -964,7 +985,7 @@ static void dev_chain_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::ve
     S.st.kernel_launches++;
     char *hm = S.ch_msa.need_geo(msa_bytes + 16);
     if (msa_bytes) CK(cudaMemcpyAsync(hm, S.c_msa.p, msa_bytes, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    slot_wait(S);
     S.t_wait += now_ms() - ts2;
     const double tf0 = now_ms();
     parallel_for(S.n_threads, np, [&](size_t i) {

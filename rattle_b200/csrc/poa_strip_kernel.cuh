@@ -44,7 +44,7 @@ struct PoaSJob {
                          // spilled rows (slot 0 = virtual start row), then halo[(n_spill+1) x n_strips] (H of the
                          // column left of the strip), then passb[n+1] (hand-over between passes), then 8 words per
                          // thread: H of the lane's best row and its best cell over all passes (value, row, column)
-    uint64_t code_off;   // u32 words into the arena: n x n_strips x 128 words
+    uint64_t code_off;   // u32 words into the arena: ceil(n/8) x n_strips x 1024 words (tiles of 8 rows, ps_code_words)
     uint32_t q_off;      // bytes into the query buffer: n_strips*256 letter codes (0..4, pad 255)
     uint32_t row_off;    // into rec: n+1 entries, entry r describes row r (1-based)
     uint32_t pred_base;  // into preds: predecessor words of rows with more than 3 predecessors
@@ -70,7 +70,11 @@ __host__ __device__ __forceinline__ size_t ps_hf_words(int n, int n_strips, int 
     return (size_t)(n_spill + 1) * n_strips * 256 + (size_t)(n_spill + 1) * n_strips + (size_t)((n + 1 + 3) & ~3) +
            (size_t)PS_MAXW * 32 * 8;
 }
-__host__ __device__ __forceinline__ size_t ps_code_words(int n, int n_strips) { return (size_t)n * n_strips * 128; }
+// traceback codes are stored in tiles of 8 graph rows x 8 columns (one lane's columns): 128 contiguous bytes, so that the
+// traceback fetches the 64 cells around its position with ONE coalesced load and walks inside the tile with shuffles
+__host__ __device__ __forceinline__ size_t ps_code_words(int n, int n_strips) {
+    return (size_t)((n + 7) / 8) * n_strips * 1024;
+}
 __host__ __device__ __forceinline__ size_t ps_smem_bytes(int n_warps, int K) {
     return (size_t)n_warps * (PS_NLET * 32 * 16 + K * 64 * 16 + 32);
 }
@@ -160,20 +164,6 @@ inline uint4 ps_lds128(ps_saddr a) {
 }
 #endif
 
-// predecessor word of (row record, index) — records keep up to three predecessors inline
-__device__ __forceinline__ uint32_t ps_pred_word(const uint4 &rc, int idx, const int32_t *pr) {
-    const int np = (int)((rc.x >> 8) & 0xffu);
-    if (idx == 0) return rc.y;
-    if (idx == 1) return rc.z;
-    if (np <= 3) return rc.w;
-    return (uint32_t)pr[rc.w + idx];
-}
-// ... and the row it names, seen from row r
-__device__ __forceinline__ int ps_pred_row(const uint4 &rc, int idx, const int32_t *pr, int r, const int32_t *spill_rows) {
-    const uint32_t w = ps_pred_word(rc, idx, pr);
-    return (w & PS_FAR) ? spill_rows[w & 0xffffu] : r - (int)w;
-}
-
 // One predecessor row (cH, cF = its H and F in my 8 columns, hl = its H left of the strip, lane 0 only) folded into
 // the running Hdiag / F of the current row.  FIRST: plain assignment, predecessor index 0.  Otherwise the strictly
 // better candidate replaces the running value and its index (first arg-max = the reference's in_edges order).
@@ -250,7 +240,8 @@ __device__ __forceinline__ void ps_align_job(const PoaSJob &J, const uint8_t *__
         const uint4 *recs = rec + J.row_off;
         const uint32_t pred_base = J.pred_base;
         const int n_pass = (nst + NW - 1) / NW;
-        const uint32_t hf_stride = (uint32_t)nst * 256u, cd_stride = (uint32_t)nst * 128u;
+        const uint32_t hf_stride = (uint32_t)nst * 256u;
+        const uint32_t cd_tile_step = (uint32_t)nst * 1024u - 28u;  // from the last row of a tile to the first of the next
 
         *reinterpret_cast<uint4 *>(mine + 4) = make_uint4(0u, 0u, 0u, 0u);
 
@@ -294,7 +285,8 @@ __device__ __forceinline__ void ps_align_job(const PoaSJob &J, const uint8_t *__
                     }
                 }
                 __syncwarp();
-                uint32_t *cd_w = cd + (size_t)t * 128 + lane * 4;  // row r of the codes
+                // codes of row r: tile (r-1)/8, inside it [strip][lane][row in tile][4 words]
+                uint32_t *cd_w = cd + ((size_t)t * 32 + lane) * 32;
                 const bool has_left = t > 0, has_right = t + 1 < nst;
                 const bool left_smem = pos > 0, right_smem = pos + 1 < NW;
                 const ps_saddr mb_in = (ps_saddr)__cvta_generic_to_shared(&s_mb[left_smem ? pos - 1 : 0][0]);
@@ -443,7 +435,7 @@ __device__ __forceinline__ void ps_align_job(const PoaSJob &J, const uint8_t *__
                         for (int k = 0; k < 4; ++k) cw[k] = dpk[k] * 2048u + cw[k];
                     }
                     *reinterpret_cast<uint4 *>(cd_w) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
-                    cd_w += cd_stride;
+                    cd_w += (r & 7) ? 4u : cd_tile_step;
                     // ---- best cell of this lane: first row with a strictly larger H (padding columns never win:
                     // they only see mismatches and gaps, so they stay below a real cell's H)
                     uint32_t hm = __vimax3_s16x2(H[0], H[1], H[2]);
@@ -538,15 +530,18 @@ k_poa_strip(const PoaSJob *__restrict__ jobs, int n_jobs, const uint8_t *__restr
 // end-to-start; the host reverses them and maps rows to node ids.  Lane k speculatively fetches the code of cell
 // (i-k, j-k); leading lanes whose move is "diagonal to row i-k-1" are committed 32 at a time, anything else takes
 // the general single step.
-// (one warp; every lane returns the number of pairs written)
+// (one warp; every lane returns the number of pairs written).  The walk is serial; what it costs is the latency of the
+// dependent loads, so the warp keeps two 128-byte tiles in registers — the codes of 8 rows x 8 columns around the
+// current cell and the row records of those 8 rows, one word per lane, each fetched with one coalesced load — and reads
+// them with shuffles: about five steps of the path per pair of loads instead of two loads per step.
 __device__ __forceinline__ int ps_traceback_warp(const PoaSJob &J, const int4 b, const uint4 *__restrict__ rec,
                                                  const int32_t *__restrict__ preds, const int32_t *__restrict__ spill_rows,
                                                  const uint32_t *__restrict__ arena, const int32_t *__restrict__ pool,
                                                  int32_t *aln_out) {
     const int lane = threadIdx.x & 31;
-    const int nst = J.n_strips;
+    const int nst = J.n_strips, n = J.n;
     const uint32_t *cd = arena + J.code_off;
-    const uint4 *recs = rec + J.row_off;
+    const uint32_t *recs32 = reinterpret_cast<const uint32_t *>(rec + J.row_off);
     const int32_t *pr = preds + J.pred_base;
     const int32_t *sp = spill_rows + J.spill_off;
     const int best = b.x;
@@ -555,82 +550,101 @@ __device__ __forceinline__ int ps_traceback_warp(const PoaSJob &J, const int4 b,
     int i = b.y, j = b.z;
     // graphs with a device mirror: report node ids (what Graph::add_alignment consumes) instead of rows
     const int32_t *order = (J.order_off != ~0ull) ? pool + J.order_off : nullptr;
-    auto node_of = [&](int row) -> int { return order ? order[row - 1] : row; };
+    int c_tile = -1, c_grp = -1, r_tile = -1;
+    uint32_t cw = 0u, rw = 0u;
     auto code_at = [&](int row, int col) -> uint32_t {  // row >= 1, col >= 1
-        const int jj = col - 1;
-        const uint32_t wv = cd[((size_t)(row - 1) * nst + (jj >> 8)) * 128 + ((jj >> 3) & 31) * 4 + (jj & 3)];
+        const int tile = (row - 1) >> 3, jj = col - 1, grp = jj >> 3;
+        if (tile != c_tile || grp != c_grp) {
+            cw = cd[((size_t)tile * nst + (grp >> 5)) * 1024 + (size_t)(grp & 31) * 32 + lane];
+            c_tile = tile;
+            c_grp = grp;
+        }
+        const uint32_t wv = __shfl_sync(0xffffffffu, cw, ((row - 1) & 7) * 4 + (jj & 3));
         return (jj & 4) ? (wv >> 16) : (wv & 0xffffu);
+    };
+    auto rec_word = [&](int row, int k) -> uint32_t {  // word k of the record of row >= 1
+        const int tile = (row - 1) >> 3;
+        if (tile != r_tile) {
+            const int rr = tile * 8 + 1 + (lane >> 2);
+            rw = rr <= n ? recs32[4 * (size_t)rr + (lane & 3)] : 0u;
+            r_tile = tile;
+        }
+        return __shfl_sync(0xffffffffu, rw, ((row - 1) & 7) * 4 + k);
+    };
+    auto pred_row = [&](int row, int idx) -> int {
+        uint32_t w;
+        if (idx == 0) w = rec_word(row, 1);
+        else if (idx == 1) w = rec_word(row, 2);
+        else {
+            const int np = (int)((rec_word(row, 0) >> 8) & 0xffu);
+            const uint32_t w3 = rec_word(row, 3);
+            w = np <= 3 ? w3 : (uint32_t)pr[w3 + idx];
+        }
+        return (w & PS_FAR) ? sp[w & 0xffffu] : row - (int)w;
+    };
+    // pairs are written with ROWS; the rows are mapped to node ids at the end, by all lanes at once (a dependent
+    // load -> store per step would stall the walk for a memory latency each time)
+    auto emit = [&](int row, int pos) {
+        if (lane == 0) {
+            out[2 * cnt] = row;
+            out[2 * cnt + 1] = pos;
+        }
+        ++cnt;
     };
     if (best > 0) {
         while (i > 0 && j > 0) {
-            const int ik = i - lane, jk = j - lane;
-            const bool valid = ik >= 1 && jk >= 1;
-            uint32_t c = 0;
-            int prow = -1;
-            if (valid) {
-                c = code_at(ik, jk);
-                const uint4 rcd = recs[ik];
-                if ((c & 3u) == 1u) prow = ps_pred_row(rcd, (int)(c >> 11), pr, ik, sp);
+            // ---- fast path: consecutive "diagonal to the previous row" steps, as far as the cached tile reaches
+            // (lane k looks at cell (i-k, j-k); in round 2 of the correction nearly the whole path is such a run)
+            {
+                const int ri = (i - 1) & 7, cj = (j - 1) & 7;
+                (void)code_at(i, j);       // tiles of (i, j) cached
+                (void)rec_word(i, 0);
+                const int m = min(ri, cj) + 1;
+                const int rk = max(ri - lane, 0), ck = max(cj - lane, 0);
+                const uint32_t wv = __shfl_sync(0xffffffffu, cw, rk * 4 + (ck & 3));
+                const uint32_t ck_code = (ck & 4) ? (wv >> 16) : (wv & 0xffffu);
+                const uint32_t dp = ck_code >> 11;
+                const uint32_t pw = __shfl_sync(0xffffffffu, rw, rk * 4 + 1 + (int)min(dp, 1u));
+                const bool chain = lane < m && (ck_code & 3u) == 1u && dp <= 1u && pw == 1u;
+                const unsigned mk = __ballot_sync(0xffffffffu, chain);
+                const int run = __ffs(~mk) - 1;
+                if (run > 0) {
+                    if (lane < run) {
+                        out[2 * (cnt + lane)] = i - lane;
+                        out[2 * (cnt + lane) + 1] = j - lane - 1;
+                    }
+                    cnt += run;
+                    i -= run;
+                    j -= run;
+                    continue;
+                }
             }
-            const bool chain = valid && (c & 3u) == 1u && prow == ik - 1;
-            const unsigned mk = __ballot_sync(0xffffffffu, chain);
-            const int run = (mk == 0xffffffffu) ? 32 : (__ffs(~mk) - 1);
-            if (lane < run) {
-                out[2 * (cnt + lane)] = node_of(ik);
-                out[2 * (cnt + lane) + 1] = jk - 1;
-            }
-            cnt += run;
-            i -= run;
-            j -= run;
-            if (run == 32) continue;
-            if (i <= 0 || j <= 0) break;
-            const uint32_t c0 = __shfl_sync(0xffffffffu, c, run);
-            const int prow0 = __shfl_sync(0xffffffffu, prow, run);
+            const uint32_t c0 = code_at(i, j);
             if (!(c0 & 1u)) break;  // H == 0
             if (!(c0 & 2u)) {       // diagonal
-                if (lane == 0) {
-                    out[2 * cnt] = node_of(i);
-                    out[2 * cnt + 1] = j - 1;
-                }
-                ++cnt;
-                i = prow0;
+                emit(i, j - 1);
+                i = pred_row(i, (int)(c0 >> 11));
                 j = j - 1;
             } else if (!(c0 & 4u)) {  // vertical; extend_up iff H == F[p][j]+e
-                if (lane == 0) {
-                    out[2 * cnt] = node_of(i);
-                    out[2 * cnt + 1] = -1;
-                }
-                ++cnt;
+                emit(i, -1);
                 const bool ext = ((c0 >> 4) & 3u) <= 1u;
-                i = ps_pred_row(recs[i], (int)((c0 >> 6) & 31u), pr, i, sp);
+                i = pred_row(i, (int)((c0 >> 6) & 31u));
                 if (ext) {
                     while (true) {  // extend_up walk (simd_alignment_engine.cpp:1388-1425)
                         const uint32_t c2 = code_at(i, j);
                         const bool stop = ((c2 >> 4) & 3u) >= 1u;  // F == H[p][j]+g
-                        if (lane == 0) {
-                            out[2 * cnt] = node_of(i);
-                            out[2 * cnt + 1] = -1;
-                        }
-                        ++cnt;
-                        i = ps_pred_row(recs[i], (int)((c2 >> 6) & 31u), pr, i, sp);
+                        emit(i, -1);
+                        i = pred_row(i, (int)((c2 >> 6) & 31u));
                         if (stop || i == 0) break;
                     }
                 }
             } else {  // horizontal; extend_left iff H == E[j-1]+e, i.e. E[j] is an extension of E[j-1]
                 const bool ext = (j >= 2) && !(code_at(i, j - 1) & 8u);
-                if (lane == 0) {
-                    out[2 * cnt] = -1;
-                    out[2 * cnt + 1] = j - 1;
-                }
-                ++cnt;
+                emit(-1, j - 1);
                 j = j - 1;
                 if (ext) {
                     while (true) {  // extend_left walk (simd_alignment_engine.cpp:1364-1387)
-                        if (lane == 0) {
-                            out[2 * cnt] = -1;
-                            out[2 * cnt + 1] = j - 1;
-                        }
-                        ++cnt;
+                        emit(-1, j - 1);
                         --j;
                         if (j < 1) break;
                         if (code_at(i, j) & 8u) break;  // E[j+1] != E[j]+e
@@ -639,6 +653,13 @@ __device__ __forceinline__ int ps_traceback_warp(const PoaSJob &J, const int4 b,
             }
         }
     }
+    __syncwarp();
+    if (order)
+        for (int x = lane; x < cnt; x += 32) {
+            const int row = out[2 * x];
+            if (row > 0) out[2 * x] = order[row - 1];
+        }
+    __syncwarp();
     return cnt;
 }
 

@@ -84,7 +84,7 @@ int main(int argc, char **argv) {
         unsigned counter = 0;
         const int smem_cap_n = sort_in_smem ? dc_sort_cap(72 * 1024) : 0;
         emu::launch(1, (unsigned)nw * 32, [&]() {
-            k_poa_chain<5, -4, -8, -6>(&P, &list0, 1, sq.data(), pool.data(), q.data(), reinterpret_cast<uint4 *>(rec.data()),
+            k_poa_chain<5, -4, -8, -6, 256, 3>(&P, &list0, 1, sq.data(), pool.data(), q.data(), reinterpret_cast<uint4 *>(rec.data()),
                                        preds.data(), spill_rows.data(), aln.data(), path.data(), qnode.data(), arena.data(),
                                        stats, &counter, K, smem_cap_n);
         });

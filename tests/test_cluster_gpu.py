@@ -240,3 +240,37 @@ def test_cluster_config2_full_size_matches_reference_digest(ctx, genes):
     assert sorted(cl.mem_id.tolist()) == list(range(rs.n))
     for c in range(0, cl.n_clusters, 37):
         assert cl.main_id[c] in cl.mem_id[cl.cl_off[c]:cl.cl_off[c + 1]]
+
+
+def test_pair_similarity_scratch_deferral_and_exhaustion(ctx, orc):
+    """survivors with more than 1024 matches sort in a global scratch arena; when it is full they are deferred to the
+    follow-up launches (scratch empty again) instead of failing the call, and only what is left after those raises"""
+    import rattle_b200
+    rng = np.random.default_rng(9)
+    core = bytes(rng.choice(list(b"ACGT"), size=2300).astype(np.uint8))
+    seqs = [core, core[3:], core[:-5], core[7:-2]]
+    rs = synth.from_sequences(seqs)
+    ctx.upload(rs.bases, rs.offsets)
+    km = [orc.extract_kmers(s, 10, True) for s in seqs]
+
+    def run(n_tasks):
+        a = [t % 4 for t in range(n_tasks)]
+        b = [(t + 1 + t // 4) % 4 for t in range(n_tasks)]
+        a, b = zip(*[(x, y) for x, y in zip(a, b) if x != y])
+        res = ctx.pair_similarity(list(a), list(b), [0] * len(a), kmer_size=10, is_rna=False)
+        return a, b, res
+
+    ctx.set_option("scratch_mb", 1)  # ~60 KB per survivor: about 16 per launch, 3 launches per call
+    try:
+        a, b, res = run(40)
+        assert res["n_common"].min() > 2000  # every task needs the arena
+        for t in range(len(a)):
+            first, second = orc.common_kmers(km[a[t]][1], km[a[t]][2], km[b[t]][1], km[b[t]][2])
+            bases, dist = orc.similarity(first, second, 10)
+            assert res["n_common"][t] == len(first) and res["bases"][t] == bases and res["n_dist"][t] == len(dist)
+            assert res["accept"][t] == 1
+        with pytest.raises(rattle_b200.RattleError) as e:
+            run(400)
+        assert e.value.code == -3
+    finally:
+        ctx.set_option("scratch_mb", 1024)
