@@ -54,6 +54,8 @@ const char *rtl_last_error(const rtl_ctx *ctx); /* ctx may be NULL: error of the
  * units (default 12; both set before the first POA call), "poa_kernel" = 1 forces the int32 POA kernel,
  * "poa_gpu_sort" = 0 keeps the graphs' topological sort and row records on the host (default 1: on the GPU),
  * "poa_mirror_pct" = capacity of the device graph mirrors in percent of the default (tests: forces the host path),
+ * "bv_kernel" = 2 sends bitvector scans with at most 16 seeds to the bulk-copy ring kernel (default: the register-staged
+ * scan, whose seed tile is staged by bulk copies),
  * "poa_device_chain" = 0 drives every alignment step from the host (default 1: whole per-pack chains run on the GPU).
  * Returns RTL_ERR_INPUT for an unknown key. */
 int rtl_set_option(rtl_ctx *ctx, const char *key, int64_t value);

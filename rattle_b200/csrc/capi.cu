@@ -112,6 +112,8 @@ int rtl_set_option(rtl_ctx *ctx, const char *key, int64_t value) {
     } else if (k == "scratch_mb") {
         if (value < 1) return RTL_ERR_INPUT;
         ctx->scratch_mb = value;
+    } else if (k == "bv_kernel") {
+        ctx->bv_kernel = (int)value;
     } else if (k == "poa_batch") {
         ctx->poa_batch = (int)value;
     } else if (k == "poa_units") {

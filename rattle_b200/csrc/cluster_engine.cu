@@ -64,7 +64,9 @@ struct ClusterState {
     int ex_k = -1, ex_both = -1;
     DevBuf<uint32_t> kh[2];
     DevBuf<int32_t> kp[2];
-    DevBuf<uint64_t> bv[2];
+    DevBuf<uint64_t> bvbuf;   // bitvectors, [read][fwd 64 words | rev 64 words] when both strands are extracted
+    uint64_t *bv[2] = {nullptr, nullptr};
+    int bv_stride = 64;
     DevBuf<int32_t> pc;
     DevBuf<uint32_t> read_list;
     DevBuf<uint64_t> long_off, long_scratch;
@@ -101,6 +103,7 @@ static void set_smem_attrs(ClusterState &S) {
     const int max_smem = 227 * 1024;
     CK(cudaFuncSetAttribute(k_extract_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CK(cudaFuncSetAttribute(k_bv_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CK(cudaFuncSetAttribute(k_bv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CK(cudaFuncSetAttribute(k_join_count, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CK(cudaFuncSetAttribute(k_pair_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     S.smem_attr_set = true;
@@ -161,8 +164,12 @@ void cluster_extract(rtl_ctx *ctx, int k, int both) {
         const bool on = s == 0 || both;
         S.kh[s].need(on ? total_k + 4 : 4);
         S.kp[s].need(on ? total_k + 4 : 4);
-        S.bv[s].need(on ? (size_t)n * 64 : 64);
     }
+    // a read's forward and reverse bitvector are adjacent: the scan fetches both with one bulk copy
+    S.bv_stride = both ? 128 : 64;
+    S.bvbuf.need((size_t)n * S.bv_stride + 128);
+    S.bv[0] = S.bvbuf.p;
+    S.bv[1] = both ? S.bvbuf.p + 64 : S.bvbuf.p + (size_t)n * 64;  // (single strand: 64 words nobody reads)
     S.pc.need(n);
     // bucket reads by padded list size
     const int n_cls = sizeof(SORT_CLASSES) / sizeof(int);
@@ -194,8 +201,8 @@ void cluster_extract(rtl_ctx *ctx, int k, int both) {
         // gridDim.x limit is 2^31-1; y = strand
         dim3 grid((unsigned)cnt, both ? 2 : 1);
         k_extract_smem<<<grid, threads, smem, st>>>(S.d_bases.p, S.d_off.p, S.read_list.p + start[c], k, n_pad,
-                                                    S.kh[0].p, S.kp[0].p, S.kh[1].p, S.kp[1].p, S.bv[0].p, S.bv[1].p,
-                                                    S.pc.p, S.flags.p);
+                                                    S.kh[0].p, S.kp[0].p, S.kh[1].p, S.kp[1].p, S.bv[0], S.bv[1],
+                                                    S.bv_stride, S.pc.p, S.flags.p);
         CK(cudaGetLastError());
         ctx->stats.kernel_launches++;
     }
@@ -219,7 +226,7 @@ void cluster_extract(rtl_ctx *ctx, int k, int both) {
             dim3 grid((unsigned)cnt, both ? 2 : 1);
             k_extract_long<<<grid, 1024, 0, st>>>(S.d_bases.p, S.d_off.p, S.read_list.p + start[n_cls], S.long_off.p,
                                                   S.long_scratch.p, k, S.kh[0].p, S.kp[0].p, S.kh[1].p, S.kp[1].p,
-                                                  S.bv[0].p, S.bv[1].p, S.pc.p, S.flags.p);
+                                                  S.bv[0], S.bv[1], S.bv_stride, S.pc.p, S.flags.p);
             CK(cudaGetLastError());
             ctx->stats.kernel_launches++;
             CK(cudaStreamSynchronize(st));  // `so` must outlive the copy
@@ -244,8 +251,9 @@ static ReadView view(ClusterState &S) {
     R.kh[1] = S.kh[1].p;
     R.kp[0] = S.kp[0].p;
     R.kp[1] = S.kp[1].p;
-    R.bv[0] = S.bv[0].p;
-    R.bv[1] = S.bv[1].p;
+    R.bv[0] = S.bv[0];
+    R.bv[1] = S.bv[1];
+    R.bv_stride = S.bv_stride;
     R.pc = S.pc.p;
     R.k = S.ex_k;
     R.n = S.n;
@@ -262,6 +270,27 @@ static void make_cut_table(double thr, std::vector<uint16_t> &cut) {
         cut[m] = (uint16_t)std::min(c, 4097);
     }
     cut[0] = 4097;
+}
+
+// launches the bitvector scan over `n_targets` targets and seed tiles covering up to `max_seeds` seeds.  Option
+// bv_kernel=2 sends scans with few seeds (the HBM-bound regime) to the bulk-copy ring kernel k_bv_stream; measured on B200
+// it streams 0.54 of the HBM peak against 0.59 of the register-staged kernel, which therefore stays the default
+static void launch_bv_scan(rtl_ctx *ctx, BvScanArgs a, int64_t n_targets, int max_seeds, cudaStream_t st) {
+    if (ctx->bv_kernel != 2 || max_seeds > BVT_TS) {
+        a.ts_cap = std::max(1, std::min(BVS_TS, max_seeds));
+        int gx = (int)std::min<int64_t>((n_targets + 15) / 16, (int64_t)ctx->n_sm * 8);
+        dim3 grid(std::max(gx, 1), (max_seeds + a.ts_cap - 1) / a.ts_cap);
+        k_bv_scan<<<grid, BVS_THREADS, (size_t)a.ts_cap * (64 * 8 + 8), st>>>(a);
+    } else {
+        a.ts_cap = std::max(1, max_seeds);
+        const size_t smem = bvt_smem_bytes(a.ts_cap);
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bv_stream, BVT_THREADS, smem));
+        const int64_t groups = (n_targets + BVT_SLOT_TGT - 1) / BVT_SLOT_TGT;
+        const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((groups + BVT_CONS - 1) / BVT_CONS, (int64_t)ctx->n_sm * std::max(1, occ)));
+        k_bv_stream<<<dim3(gx, 1), BVT_THREADS, smem, st>>>(a);
+    }
+    CK(cudaGetLastError());
 }
 
 static const int JC_CAP_W = 1760;   // staged hashes (list B) per warp in k_join_count: 16 warps x 6.9 KB, 2 CTAs per SM
@@ -391,8 +420,9 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
         // ---- phase A: candidates x candidates
         {
             BvScanArgs a{};
-            a.bv_f = S.bv[0].p;
-            a.bv_r = S.bv[1].p;
+            a.bv_f = S.bv[0];
+            a.bv_r = S.bv[1];
+            a.bv_stride = S.bv_stride;
             a.pc = S.pc.p;
             a.item_read = d_item_read;
             a.seed_item = S.cand.p;
@@ -414,10 +444,8 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
             a.task_cap = (int64_t)S.tasks.cap;
             a.ovf = S.flags.p + 1;
             a.pair_counter = S.counters.p + 3;
-            dim3 grid((W + 15) / 16, (W + BVS_TS - 1) / BVS_TS);  // 8 warps x 2 targets per CTA iteration
             S.ev.begin(EV_BV, st);
-            k_bv_scan<<<grid, BVS_THREADS, BVS_TS * 64 * 8 + BVS_TS * 8, st>>>(a);
-            CK(cudaGetLastError());
+            launch_bv_scan(ctx, a, W, W, st);
             S.ev.end(EV_BV, st);
             ctx->stats.kernel_launches++;
             ctx->stats.bv_launches++;
@@ -443,8 +471,9 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
             const int64_t c1 = std::min<int64_t>(x_hi, c0 + chunk);
             CK(cudaMemsetAsync(S.counters.p, 0, 3 * sizeof(unsigned long long), st));
             BvScanArgs a{};
-            a.bv_f = S.bv[0].p;
-            a.bv_r = S.bv[1].p;
+            a.bv_f = S.bv[0];
+            a.bv_r = S.bv[1];
+            a.bv_stride = S.bv_stride;
             a.pc = S.pc.p;
             a.item_read = d_item_read;
             a.seed_item = S.seed_item.p;
@@ -466,12 +495,8 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
             a.task_cap = (int64_t)S.tasks.cap;
             a.ovf = S.flags.p + 1;
             a.pair_counter = S.counters.p + 3;
-            const int64_t nt = c1 - c0;
-            int gx = (int)std::min<int64_t>((nt + 15) / 16, (int64_t)ctx->n_sm * 8);
-            dim3 grid(gx, (W + BVS_TS - 1) / BVS_TS);
             S.ev.begin(EV_BV, st);
-            k_bv_scan<<<grid, BVS_THREADS, BVS_TS * 64 * 8 + BVS_TS * 8, st>>>(a);
-            CK(cudaGetLastError());
+            launch_bv_scan(ctx, a, c1 - c0, W, st);
             S.ev.end(EV_BV, st);
             ctx->stats.kernel_launches++;
             ctx->stats.bv_launches++;
@@ -659,10 +684,10 @@ void cluster_download_kmers(rtl_ctx *ctx, uint32_t *fh, int32_t *fp, uint32_t *r
     if (S.ex_both) {
         if (rh) CK(cudaMemcpyAsync(rh, S.kh[1].p, total_k * 4, cudaMemcpyDeviceToHost, st));
         if (rp) CK(cudaMemcpyAsync(rp, S.kp[1].p, total_k * 4, cudaMemcpyDeviceToHost, st));
-        if (br) CK(cudaMemcpyAsync(br, S.bv[1].p, (size_t)S.n * 512, cudaMemcpyDeviceToHost, st));
+        if (br) CK(cudaMemcpy2DAsync(br, 512, S.bv[1], (size_t)S.bv_stride * 8, 512, S.n, cudaMemcpyDeviceToHost, st));
     } else if (br)
         memset(br, 0, (size_t)S.n * 512);
-    if (bf) CK(cudaMemcpyAsync(bf, S.bv[0].p, (size_t)S.n * 512, cudaMemcpyDeviceToHost, st));
+    if (bf) CK(cudaMemcpy2DAsync(bf, 512, S.bv[0], (size_t)S.bv_stride * 8, 512, S.n, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
 }
 
@@ -694,8 +719,9 @@ void cluster_bv_scan_dense(rtl_ctx *ctx, int k, int is_rna, const int32_t *seed_
     CK(cudaMemsetAsync(d_cnt.need(2), 0, 16, st));
     CK(cudaMemsetAsync(d_ovf.need(1), 0, 4, st));
     BvScanArgs a{};
-    a.bv_f = S.bv[0].p;
-    a.bv_r = S.bv[1].p;
+    a.bv_f = S.bv[0];
+    a.bv_r = S.bv[1];
+    a.bv_stride = S.bv_stride;
     a.pc = S.pc.p;
     a.item_read = nullptr;
     a.seed_item = d_seeds.p;
@@ -709,19 +735,15 @@ void cluster_bv_scan_dense(rtl_ctx *ctx, int k, int is_rna, const int32_t *seed_
     a.order_check = 0;
     a.rank = 0;
     a.world = 1;
-    a.ts_cap = std::max(1, std::min(BVS_TS, n_seeds));
     a.tasks = nullptr;
     a.n_tasks = d_cnt.p;
     a.ovf = d_ovf.p;
     a.dense_common = common ? d_common.p : nullptr;  // NULL outputs: scan only (timing runs)
     a.dense_pass = pass ? d_pass.p : nullptr;
     a.pair_counter = d_cnt.p + 1;
-    int gx = (int)std::min<int64_t>(((int64_t)n_targets + 15) / 16, (int64_t)ctx->n_sm * 8);
-    dim3 grid(std::max(gx, 1), (n_seeds + a.ts_cap - 1) / a.ts_cap);
     S.ev.acc[EV_BV] = 0;
     S.ev.begin(EV_BV, st);
-    k_bv_scan<<<grid, BVS_THREADS, (size_t)a.ts_cap * (64 * 8 + 8), st>>>(a);
-    CK(cudaGetLastError());
+    launch_bv_scan(ctx, a, n_targets, n_seeds, st);
     S.ev.end(EV_BV, st);
     unsigned long long hcnt[2] = {0, 0};
     CK(cudaMemcpyAsync(hcnt, d_cnt.p, 16, cudaMemcpyDeviceToHost, st));

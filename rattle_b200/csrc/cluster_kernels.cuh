@@ -19,10 +19,11 @@ struct ReadView {
     const int32_t *len;    // n
     const uint32_t *kh[2]; // sorted k-mer hashes, forward / reverse-complement strand
     const int32_t *kp[2];  // positions
-    const uint64_t *bv[2]; // n x 64
+    const uint64_t *bv[2]; // read r's 64 words at bv[s] + r * bv_stride (both strands interleaved: stride 128)
     const int32_t *pc;     // popcount of bv[0]
     int k;
     uint32_t n;
+    int bv_stride;
     __device__ __forceinline__ uint64_t koff(uint32_t r) const { return off[r] - (uint64_t)k * r; }
 };
 
@@ -37,7 +38,7 @@ __device__ __forceinline__ int base_code(uint8_t c) {
 // smem: keys[n_pad] u64 | bvw[128] u32 | codes[n_pad+32] u8
 __global__ void k_extract_smem(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ off,
                                const uint32_t *__restrict__ read_list, int k, int n_pad, uint32_t *kh_f, int32_t *kp_f,
-                               uint32_t *kh_r, int32_t *kp_r, uint64_t *bv_f, uint64_t *bv_r, int32_t *pc, int *err) {
+                               uint32_t *kh_r, int32_t *kp_r, uint64_t *bv_f, uint64_t *bv_r, int bv_stride, int32_t *pc, int *err) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     uint64_t *keys = (uint64_t *)sm_raw;
     uint32_t *bvw = (uint32_t *)(keys + n_pad);
@@ -101,7 +102,7 @@ __global__ void k_extract_smem(const uint8_t *__restrict__ bases, const uint64_t
         kp[ko + p] = (int32_t)(uint32_t)key;
     }
     uint64_t *bv = strand ? bv_r : bv_f;
-    if (tid < 64) bv[(uint64_t)r * 64 + tid] = (uint64_t)bvw[2 * tid] | ((uint64_t)bvw[2 * tid + 1] << 32);
+    if (tid < 64) bv[(uint64_t)r * bv_stride + tid] = (uint64_t)bvw[2 * tid] | ((uint64_t)bvw[2 * tid + 1] << 32);
     if (strand == 0 && tid < 32) {
         int c = 0;
 #pragma unroll
@@ -116,7 +117,7 @@ __global__ void k_extract_smem(const uint8_t *__restrict__ bases, const uint64_t
 __global__ void k_extract_long(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ off,
                                const uint32_t *__restrict__ read_list, const uint64_t *__restrict__ scratch_off,
                                uint64_t *scratch, int k, uint32_t *kh_f, int32_t *kp_f, uint32_t *kh_r, int32_t *kp_r,
-                               uint64_t *bv_f, uint64_t *bv_r, int32_t *pc, int *err) {
+                               uint64_t *bv_f, uint64_t *bv_r, int bv_stride, int32_t *pc, int *err) {
     __shared__ uint32_t bvw[128];
     const uint32_t r = read_list[blockIdx.x];
     const int strand = blockIdx.y;
@@ -176,7 +177,7 @@ __global__ void k_extract_long(const uint8_t *__restrict__ bases, const uint64_t
         kp[ko + p] = (int32_t)(uint32_t)key;
     }
     uint64_t *bv = strand ? bv_r : bv_f;
-    if (tid < 64) bv[(uint64_t)r * 64 + tid] = (uint64_t)bvw[2 * tid] | ((uint64_t)bvw[2 * tid + 1] << 32);
+    if (tid < 64) bv[(uint64_t)r * bv_stride + tid] = (uint64_t)bvw[2 * tid] | ((uint64_t)bvw[2 * tid + 1] << 32);
     if (strand == 0 && tid < 32) {
         int c = 0;
         for (int w = 0; w < 4; ++w) c += __popc(bvw[tid * 4 + w]);
@@ -257,6 +258,7 @@ constexpr int BVS_TS = 128;       // seeds per shared-memory tile (64 KB)
 constexpr int BVS_THREADS = 256;  // 8 warps
 struct BvScanArgs {
     const uint64_t *bv_f, *bv_r;
+    int bv_stride;             // uint64 words between consecutive reads' bitvectors (128: [fwd 64 | rev 64] per read)
     const int32_t *pc;
     const int32_t *item_read;  // nullable
     const int32_t *seed_item;  // n_seeds (device count in *n_seeds_p)
@@ -281,6 +283,35 @@ struct BvScanArgs {
     unsigned long long *pair_counter;  // evaluated pairs
 };
 
+// mbarrier + bulk-copy (TMA) primitives
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{ .reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy (bytes: multiple of 16, both addresses 16-byte aligned); completes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 __global__ void __launch_bounds__(BVS_THREADS) k_bv_scan(BvScanArgs A) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int TS = A.ts_cap;
@@ -292,19 +323,28 @@ __global__ void __launch_bounds__(BVS_THREADS) k_bv_scan(BvScanArgs A) {
     if (s0 >= n_seeds) return;
     const int ts = min(TS, n_seeds - s0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < ts * 64; i += BVS_THREADS) {
-        int s = i >> 6;
-        int it = A.seed_item[s0 + s];
-        uint32_t rd = A.item_read ? (uint32_t)A.item_read[it] : (uint32_t)it;
-        sseed[i] = A.bv_f[(uint64_t)rd * 64 + (i & 63)];
-    }
-    for (int s = tid; s < ts; s += BVS_THREADS) {
-        int it = A.seed_item[s0 + s];
-        uint32_t rd = A.item_read ? (uint32_t)A.item_read[it] : (uint32_t)it;
-        sitem[s] = it;
-        spc[s] = A.pc[rd];
+    // the seed tile comes in through the bulk-copy engine (TMA): one 512-byte copy per seed, completion on an mbarrier
+    __shared__ unsigned long long s_seedbar;
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&s_seedbar);
+    if (tid == 0) {
+        mbar_init(bar_s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (tid == 0) mbar_arrive_expect_tx(bar_s, (uint32_t)ts * 512u);
+    __syncthreads();
+    {
+        const uint32_t seed_s = (uint32_t)__cvta_generic_to_shared(sseed);
+        for (int s = tid; s < ts; s += BVS_THREADS) {
+            const int it = A.seed_item[s0 + s];
+            const uint32_t rd = A.item_read ? (uint32_t)A.item_read[it] : (uint32_t)it;
+            sitem[s] = it;
+            spc[s] = A.pc[rd];
+            bulk_g2s(seed_s + (uint32_t)s * 512u, A.bv_f + (uint64_t)rd * A.bv_stride, 512u, bar_s);
+        }
+    }
+    __syncthreads();
+    mbar_wait(bar_s, 0);
     int n_t = A.tgt_list ? (A.n_tgt_p ? *A.n_tgt_p : A.t1) : (A.t1 - A.t0);
     unsigned long long my_pairs = 0;
     // Half a warp per target (two targets per warp iteration): every lane holds 32 bytes of the target's forward
@@ -350,11 +390,11 @@ __global__ void __launch_bounds__(BVS_THREADS) k_bv_scan(BvScanArgs A) {
         t.pcj = 0;
         t.live = p.live;
         if (!p.live) return t;
-        const ulonglong2 *pf = reinterpret_cast<const ulonglong2 *>(A.bv_f + (uint64_t)p.rd * 64 + 4 * sub);
+        const ulonglong2 *pf = reinterpret_cast<const ulonglong2 *>(A.bv_f + (uint64_t)p.rd * A.bv_stride + 4 * sub);
         t.f0 = pf[0];
         t.f1 = pf[1];
         if (A.both) {
-            const ulonglong2 *pr = reinterpret_cast<const ulonglong2 *>(A.bv_r + (uint64_t)p.rd * 64 + 4 * sub);
+            const ulonglong2 *pr = reinterpret_cast<const ulonglong2 *>(A.bv_r + (uint64_t)p.rd * A.bv_stride + 4 * sub);
             t.r0 = pr[0];
             t.r1 = pr[1];
         }
@@ -425,6 +465,215 @@ __global__ void __launch_bounds__(BVS_THREADS) k_bv_scan(BvScanArgs A) {
                 }
             }
         }
+    }
+    if (lane == 0 && my_pairs && A.pair_counter) atomicAdd(A.pair_counter, my_pairs);
+}
+
+
+// ------------------------------------------------------------------------------------------------ K3, streaming regime
+// The same scan for FEW seeds (at most BVT_TS), where the kernel is bound by HBM bandwidth: the reads' bitvectors are
+// streamed through a shared-memory ring by the bulk-copy engine (TMA, cp.async.bulk + mbarrier).  Two producer warps
+// resolve which reads the next targets are (target list, taken flag, cluster -> representative) and issue one 512-byte
+// bulk copy per strand and target into the ring, far ahead of the six consumer warps, so that the bytes in flight do
+// not depend on registers and the consumers spend ~40 warp instructions per 1-KB target (the register-staged kernel
+// above needs ~240 and is issue-bound in this regime).  The seeds' bitvectors come in by bulk copies too.
+// A consumer warp takes one ring slot = 4 targets, a quarter-warp per target: a lane holds 64 B of the target's forward
+// and reverse bitvector and scores a seed with 4 LDS.128 (the seed; broadcast across the quarters) + 16 AND + 16 POPC.64.
+// Every slot has ONE producer and ONE consumer (slot (c, d) = consumer c, iteration parity d = producer d), so that
+// each mbarrier is waited on in phase order by a single warp.
+constexpr int BVT_THREADS = 256;   // warps 0-1 produce, warps 2-7 consume
+constexpr int BVT_PROD = 2, BVT_CONS = 6;
+constexpr int BVT_SLOT_TGT = 4;    // targets per ring slot
+constexpr int BVT_SLOT_BYTES = BVT_SLOT_TGT * 1024;
+constexpr int BVT_RING = BVT_CONS * BVT_PROD;  // 12 slots = 48 KB of bitvectors in flight per CTA
+constexpr int BVT_TS = 16;         // seeds at most
+
+__host__ __device__ __forceinline__ size_t bvt_smem_bytes(int ts) {
+    return (size_t)ts * 512 + (size_t)ts * 8 + (size_t)BVT_RING * BVT_SLOT_BYTES + (size_t)BVT_RING * BVT_SLOT_TGT * 16 +
+           (size_t)(2 * BVT_RING + 1) * 8 + 128;
+}
+
+__global__ void __launch_bounds__(BVT_THREADS, 3) k_bv_stream(BvScanArgs A) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];  // (dynamic shared memory starts 1024-byte aligned)
+    const int TS = A.ts_cap;
+    const int n_seeds = *A.n_seeds_p;
+    const int s0 = blockIdx.y * TS;
+    if (s0 >= n_seeds) return;
+    const int ts = min(TS, n_seeds - s0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // layout: seeds [TS][512 B] | ring [12][4][fwd 512 | rev 512] | sitem [TS] | spc [TS] | meta [12][4] int4 | barriers
+    unsigned char *sseed = sm_raw;
+    unsigned char *ring = sseed + (size_t)TS * 512;
+    int32_t *sitem = (int32_t *)(ring + (size_t)BVT_RING * BVT_SLOT_BYTES);
+    int32_t *spc = sitem + TS;
+    int4 *meta = (int4 *)(((uintptr_t)(spc + TS) + 15) & ~(uintptr_t)15);
+    unsigned long long *bars = (unsigned long long *)(meta + BVT_RING * BVT_SLOT_TGT);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t seed_s = (uint32_t)__cvta_generic_to_shared(sseed);
+    const uint32_t full_s = (uint32_t)__cvta_generic_to_shared(bars);  // [12]
+    const uint32_t empty_s = full_s + BVT_RING * 8;                     // [12]
+    const uint32_t seedbar_s = empty_s + BVT_RING * 8;
+    if (tid == 0) {
+        for (int i = 0; i < BVT_RING; ++i) {
+            mbar_init(full_s + i * 8, 1);
+            mbar_init(empty_s + i * 8, 1);
+        }
+        mbar_init(seedbar_s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // ---- seeds: one bulk copy each
+    if (tid == 0) mbar_arrive_expect_tx(seedbar_s, (uint32_t)ts * 512u);
+    __syncthreads();
+    for (int s = tid; s < ts; s += BVT_THREADS) {
+        const int it = A.seed_item[s0 + s];
+        const uint32_t rd = A.item_read ? (uint32_t)A.item_read[it] : (uint32_t)it;
+        sitem[s] = it;
+        spc[s] = A.pc[rd];
+        bulk_g2s(seed_s + (uint32_t)s * 512u, A.bv_f + (uint64_t)rd * A.bv_stride, 512u, seedbar_s);
+    }
+    __syncthreads();
+    const int n_t = A.tgt_list ? (A.n_tgt_p ? *A.n_tgt_p : A.t1) : (A.t1 - A.t0);
+    const long long n_groups = ((long long)n_t + BVT_SLOT_TGT - 1) / BVT_SLOT_TGT;
+    const uint32_t per_tgt = A.both ? 1024u : 512u;
+
+    if (warp < BVT_PROD) {
+        // ---------------- producers: warp p fills the slots of the iterations it = p, p+2, ... (6 slots = 24 targets each)
+        const int sub = lane & 3, c = lane >> 2;  // quad c feeds consumer c
+        for (int it = warp;; it += BVT_PROD) {
+            if ((long long)blockIdx.x + (long long)it * BVT_CONS * gridDim.x >= n_groups) break;  // warp-uniform
+            const long long q = (long long)blockIdx.x + ((long long)it * BVT_CONS + c) * gridDim.x;
+            const bool slot_valid = c < BVT_CONS && q < n_groups;
+            const int slot = c * BVT_PROD + warp, use = it / BVT_PROD;
+            const long long x = q * BVT_SLOT_TGT + sub;
+            int tslot = 0, item = 0, pcj = 0;
+            uint32_t rd = 0;
+            bool live = false;
+            if (slot_valid && x < n_t) {
+                tslot = A.tgt_list ? (int)x : A.t0 + (int)x;
+                item = A.tgt_list ? A.tgt_list[x] : tslot;
+                bool mine = true;
+                if (A.world > 1 && !A.presharded &&
+                    ((A.memo.item_rid ? A.memo.item_rid[item] : item) % A.world) != A.rank)
+                    mine = false;
+                if (mine && !(A.taken && A.taken[item] != 0)) {
+                    rd = A.item_read ? (uint32_t)A.item_read[item] : (uint32_t)item;
+                    pcj = A.pc[rd];
+                    live = true;
+                }
+            }
+            if (slot_valid && use > 0) mbar_wait(empty_s + slot * 8, (uint32_t)((use - 1) & 1));
+            if (slot_valid) meta[slot * BVT_SLOT_TGT + sub] = make_int4(tslot, item, pcj, live ? 1 : 0);
+            const unsigned lm = __ballot_sync(0xffffffffu, live);
+            const int nlive = __popc((lm >> (c * 4)) & 0xfu);
+            // a read's forward and reverse bitvectors are adjacent in memory (one copy per target), and the four reads
+            // of a slot are often consecutive (unclustered stretches of the initial pass): then ONE 4-KB copy fills the slot
+            const uint32_t rd0 = __shfl_sync(0xffffffffu, rd, lane & ~3);
+            const bool seq = A.both && live && rd == rd0 + (uint32_t)sub;
+            const unsigned sm = __ballot_sync(0xffffffffu, seq);
+            const bool whole = ((sm >> (c * 4)) & 0xfu) == 0xfu;
+            __syncwarp();
+            if (slot_valid && sub == 0) {
+                if (nlive) mbar_arrive_expect_tx(full_s + slot * 8, (uint32_t)nlive * per_tgt);
+                else mbar_arrive(full_s + slot * 8);
+            }
+            __syncwarp();
+            const uint32_t dst = ring_s + (uint32_t)slot * BVT_SLOT_BYTES + (uint32_t)sub * 1024u;
+            if (whole) {
+                if (sub == 0) bulk_g2s(dst, A.bv_f + (uint64_t)rd * A.bv_stride, 4096u, full_s + slot * 8);
+            } else if (live) {
+                if (A.both && A.bv_r == A.bv_f + 64) {
+                    bulk_g2s(dst, A.bv_f + (uint64_t)rd * A.bv_stride, 1024u, full_s + slot * 8);
+                } else {
+                    bulk_g2s(dst, A.bv_f + (uint64_t)rd * A.bv_stride, 512u, full_s + slot * 8);
+                    if (A.both) bulk_g2s(dst + 512u, A.bv_r + (uint64_t)rd * A.bv_stride, 512u, full_s + slot * 8);
+                }
+            }
+        }
+        return;
+    }
+    // ---------------- consumers: warp 2 + c takes slot (c, it & 1) of every iteration
+    mbar_wait(seedbar_s, 0);
+    const int c = warp - BVT_PROD;
+    const int qt = lane >> 3, j = lane & 7;  // quarter-warp qt owns target qt of the slot; lane j holds bytes [64j, 64j+64)
+    unsigned long long my_pairs = 0;
+    for (int it = 0;; ++it) {
+        const long long q = (long long)blockIdx.x + ((long long)it * BVT_CONS + c) * gridDim.x;
+        if (q >= n_groups) break;
+        const int slot = c * BVT_PROD + (it & 1);
+        mbar_wait(full_s + slot * 8, (uint32_t)((it >> 1) & 1));
+        const int4 m = meta[slot * BVT_SLOT_TGT + qt];
+        const bool live = m.w != 0;
+        const int tslot = m.x, item = m.y, pcj = m.z;
+        const long long x = q * BVT_SLOT_TGT + qt;
+        if (__any_sync(0xffffffffu, live)) {
+            ulonglong2 f[4], r[4];
+            const ulonglong2 *tp =
+                reinterpret_cast<const ulonglong2 *>(ring + (size_t)slot * BVT_SLOT_BYTES + (size_t)qt * 1024 + (size_t)j * 64);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                f[w] = live ? tp[w] : make_ulonglong2(0, 0);
+                r[w] = (live && A.both) ? tp[32 + w] : make_ulonglong2(0, 0);
+            }
+            for (int g = 0; g < ts; g += 8) {
+                uint32_t mine = 0;
+                const int lim = min(8, ts - g);
+                for (int k = 0; k < lim; ++k) {
+                    const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(sseed + (size_t)(g + k) * 512 + (size_t)j * 64);
+                    uint32_t cf = 0, cr = 0;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const ulonglong2 sv = sp[w];
+                        cf += (uint32_t)(__popcll(sv.x & f[w].x) + __popcll(sv.y & f[w].y));
+                        cr += (uint32_t)(__popcll(sv.x & r[w].x) + __popcll(sv.y & r[w].y));
+                    }
+                    uint32_t cc = cf | (cr << 16);
+#pragma unroll
+                    for (int sft = 4; sft > 0; sft >>= 1) cc += __shfl_xor_sync(0xffffffffu, cc, sft);
+                    if (j == k) mine = cc;
+                }
+                const int s = g + j;
+                bool valid = live && j < lim;
+                if (valid && A.order_check) valid = sitem[s] < item;
+                const uint32_t cf = mine & 0xffffu, cr = mine >> 16;
+                bool pf = false, pr = false;
+                if (valid) {
+                    const int mmax = max(spc[s], pcj);
+                    const uint32_t cutv = A.cut[mmax];
+                    pf = cf >= cutv;
+                    pr = A.both && cr >= cutv;
+                    if (pf && A.memo.known_failure((uint32_t)sitem[s], (uint32_t)item, 0)) pf = false;
+                    if (pr && A.memo.known_failure((uint32_t)sitem[s], (uint32_t)item, 1)) pr = false;
+                }
+                my_pairs += (unsigned long long)__popc(__ballot_sync(0xffffffffu, valid));
+                if (A.dense_common) {
+                    if (live && j < lim) {
+                        const size_t idx = (size_t)(s0 + s) * (size_t)n_t + (size_t)x;
+                        A.dense_common[idx] = mine;
+                        A.dense_pass[idx] = (uint8_t)((pf ? 1 : 0) | (pr ? 2 : 0));
+                    }
+                }
+                if (A.tasks) {
+                    const uint32_t mf = __ballot_sync(0xffffffffu, pf), mr = __ballot_sync(0xffffffffu, pr);
+                    const int tot = __popc(mf) + __popc(mr);
+                    if (tot) {
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(A.n_tasks, (unsigned long long)tot);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (base + tot > (unsigned long long)A.task_cap) {
+                            if (lane == 0) atomicExch(A.ovf, 1);
+                        } else {
+                            const uint32_t below = (1u << lane) - 1u;
+                            if (pf) A.tasks[base + __popc(mf & below)] = make_task((uint32_t)(s0 + s), 0, (uint32_t)tslot);
+                            if (pr)
+                                A.tasks[base + __popc(mf) + __popc(mr & below)] = make_task((uint32_t)(s0 + s), 1, (uint32_t)tslot);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_s + slot * 8);
     }
     if (lane == 0 && my_pairs && A.pair_counter) atomicAdd(A.pair_counter, my_pairs);
 }

@@ -123,6 +123,7 @@ struct rtl_ctx {
     int wave = 512;
     int64_t task_cap = 32ll << 20;
     int64_t scratch_mb = 1024;
+    int bv_kernel = 0;         // 2 = scans with at most 16 seeds use the bulk-copy ring kernel k_bv_stream (default: k_bv_scan)
     int poa_batch = 0;
     int poa_units = 0;         // 0 = 12 concurrently running units (set before the first POA call)
     int poa_gpu_sort = 1;      // 1 = graphs are sorted and their row records built on the GPU (poa_devgraph.cuh), 0 = on the host

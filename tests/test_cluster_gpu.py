@@ -274,3 +274,38 @@ def test_pair_similarity_scratch_deferral_and_exhaustion(ctx, orc):
         assert e.value.code == -3
     finally:
         ctx.set_option("scratch_mb", 1024)
+
+
+def test_bulk_copy_ring_scan_matches_numpy_and_clusters(ctx, orc):
+    """option bv_kernel=2: scans with at most 16 seeds run k_bv_stream (bitvectors streamed through a shared-memory ring
+    by cp.async.bulk + mbarrier): same counts / pass flags as numpy popcounts — on consecutive targets (one 4-KB copy per
+    slot), scattered ones and a ragged tail, both strands and RNA — and the same clusters with 7-seed waves"""
+    rs = small_set(seed=19, genes=18, per=11)
+    k = 10
+    popc = np.vectorize(lambda w: bin(int(w)).count("1"))
+    bvs = [orc.extract_kmers(rs.seq(i), k, True) for i in range(rs.n)]
+    bf = np.stack([b[5] for b in bvs]); br = np.stack([b[6] for b in bvs])
+    pc = popc(bf).sum(1)
+    ctx.set_option("bv_kernel", 2)
+    try:
+        for is_rna in (False, True):
+            ctx.upload(rs.bases, rs.offsets)
+            for seeds, targets in ((np.array([3, 50, 121], np.int32), np.arange(rs.n, dtype=np.int32)),
+                                   (np.arange(0, 16, dtype=np.int32), np.arange(rs.n - 3, -1, -2, dtype=np.int32)),
+                                   (np.array([7], np.int32), np.arange(5, 42, dtype=np.int32))):
+                cf, cr, passed = ctx.bv_scan(seeds, targets, 0.30000000000000004, kmer_size=k, is_rna=is_rna)
+                for si, s in enumerate(seeds):
+                    ecf = popc(bf[s][None, :] & bf[targets]).sum(1)
+                    assert np.array_equal(cf[si], ecf)
+                    mmax = np.maximum(pc[s], pc[targets]).astype(np.float64)
+                    assert np.array_equal(passed[si] & 1, (ecf / mmax >= 0.30000000000000004).astype(np.uint8))
+                    if not is_rna:
+                        ecr = popc(bf[s][None, :] & br[targets]).sum(1)
+                        assert np.array_equal(cr[si], ecr)
+                        assert np.array_equal(passed[si] >> 1, (ecr / mmax >= 0.30000000000000004).astype(np.uint8))
+        ctx.set_option("wave", 7)
+        got = ctx.cluster_reads(rs.bases, rs.offsets, is_rna=False)
+        assert_same_clusters(got, orc.cluster_reads(rs.bases, rs.offsets, is_rna=False, n_threads=8))
+    finally:
+        ctx.set_option("wave", 512)
+        ctx.set_option("bv_kernel", 0)

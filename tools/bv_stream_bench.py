@@ -36,11 +36,14 @@ def main():
     ap.add_argument("--seeds", default="1,2,4,8,32,128,512")
     ap.add_argument("--rna", action="store_true")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--kernel", type=int, default=0, help="0 = k_bv_scan (default path), 2 = bulk-copy ring scan k_bv_stream for at most 16 seeds")
     args = ap.parse_args()
     import rattle_b200
     rs = synth.config2(n_genes=args.genes).sorted_by_length()[0]
     S = 1 if args.rna else 2
     ctx = rattle_b200.Context(0)
+    ctx.set_option("bv_kernel", args.kernel)
+    tile = 128
     ctx.upload(rs.bases, rs.offsets)
     targets = np.arange(rs.n, dtype=np.int32)
     hbm, src = peak()
@@ -52,9 +55,9 @@ def main():
             st = ctx.stats()
             best = st["bv_ms"] if best is None else min(best, st["bv_ms"])
         pairs = ns * rs.n
-        tiles = (ns + 127) // 128
+        tiles = (ns + tile - 1) // tile
         dram = tiles * rs.n * (512 * S + 4)  # every seed tile streams every read's bitvectors once
-        print(json.dumps({"seeds": ns, "reads": rs.n, "strands": S, "kernel_ms": best,
+        print(json.dumps({"kernel": "k_bv_stream" if (args.kernel == 2 and ns <= 16) else "k_bv_scan", "seeds": ns, "reads": rs.n, "strands": S, "kernel_ms": best,
                           "pairs_per_s": pairs / (best * 1e-3),
                           "streamed_GBps": dram / (best * 1e-3) / 1e9, "streamed_frac_of_hbm": dram / (best * 1e-3) / 1e9 / hbm,
                           "algorithmic_GBps": pairs * (512 * S + 4) / (best * 1e-3) / 1e9, "hbm_peak": hbm, "peak_source": src}))
