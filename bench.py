@@ -147,12 +147,16 @@ def golden_form_digests(out):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def ref_sample_genes(args):
-    """bounded CPU sample: ~20 s of reference work per step on this box (cluster ~quadratic, correct linear in reads)"""
+def ref_sample_genes(args, steps=None):
+    """bounded CPU sample of the reference arm: the whole (warmup + steps) run has to end within a few minutes, so one
+    step gets min(20 s, 300 s / (warmup + steps)) of reference work; measured on the bench box: 0.75 genes (x 50
+    reads) per core and second (correct dominates at these sizes and is linear in reads, clustering ~quadratic)"""
     if args.ref_genes > 0:
         return args.ref_genes
     cores = os.cpu_count() or 1
-    return int(min(2000, max(60, 15 * cores)))
+    n = max(1, steps if steps is not None else args.warmup + args.steps)
+    per_step_s = min(20.0, 300.0 / n)
+    return int(min(2000, max(40, 0.75 * cores * per_step_s)))
 
 
 def reference_arm(args, rank, world):
@@ -168,7 +172,7 @@ def reference_arm(args, rank, world):
     genes = ref_sample_genes(args)
     rs = make_workload(genes)
     sample = ("same generator at %d genes x 50 = %d reads (~1.5 kb cDNA), cluster%s, %d threads; sample sized to the "
-              "core count (15 genes per core) so that one step is ~20 s" % (genes, rs.n, "+correct" if args.correct else "",
+              "core count and to warmup+steps so that the whole run is <= ~5 min" % (genes, rs.n, "+correct" if args.correct else "",
                                                                              cores))
     times = []
     for it in range(args.warmup + args.steps):
@@ -460,7 +464,7 @@ def main():
         try:
             import oracle
             cores = os.cpu_count() or 1
-            genes = ref_sample_genes(args)
+            genes = ref_sample_genes(args, steps=1)
             srs = make_workload(genes)
             if oracle.have_ref():
                 lib, kind = oracle.reference(), "reference"
