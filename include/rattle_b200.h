@@ -102,6 +102,19 @@ int rtl_cluster_reads(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, 
                       double repr_percentile, int is_rna, int32_t *main_id, uint8_t *main_rev, int64_t *cl_off,
                       int32_t *mem_id, uint8_t *mem_rev, int32_t *n_clusters);
 
+/* Batched cluster_reads(): the read set is the concatenation of n_seg independent read sets ("segments": reads
+ * seg_off[s] .. seg_off[s+1]-1, each already in visitation order), clustered as n_seg separate cluster_reads() calls with
+ * the same parameters would — the per-gene loop of `rattle cluster --iso` (/root/reference/main.cpp:281-324, call at :300)
+ * — but in ONE pass: one upload, one extraction, and greedy waves that span segments (pairs only exist inside a
+ * segment).  Clusters come out segment after segment: those of segment s are seg_cl_off[s] .. seg_cl_off[s+1]-1
+ * (seg_cl_off holds n_seg+1 entries), and their seq_ids count from the segment's first read, as the reference's would.
+ * Ignores rtl_set_shard: segments are what a multi-GPU caller distributes, not pairs. */
+int rtl_cluster_reads_batched(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, uint32_t n_reads,
+                              const uint32_t *seg_off, uint32_t n_seg, int kmer_size, double t_s, double t_v,
+                              double bv_threshold, double min_bv_threshold, double bv_falloff, double repr_percentile,
+                              int is_rna, int32_t *main_id, uint8_t *main_rev, int64_t *cl_off, int32_t *mem_id,
+                              uint8_t *mem_rev, int32_t *n_clusters, int64_t *seg_cl_off);
+
 /* The same in two steps, so that a caller (bench.py `value`) can time the device-resident part alone:
  * upload = H2D of bases/offsets; run = extraction + all passes + D2H of the (small) result. */
 int rtl_reads_upload(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, uint32_t n_reads);

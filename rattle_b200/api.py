@@ -37,6 +37,7 @@ ALLREDUCE_FN = ctypes.CFUNCTYPE(c_i, c_p, c_p, c_i64)
 
 # every symbol include/rattle_b200.h declares (tests/test_boundary.py checks the header against this list)
 SYMBOLS = ["rtl_init", "rtl_destroy", "rtl_last_error", "rtl_set_option", "rtl_set_stream", "rtl_get_stats", "rtl_cluster_reads",
+           "rtl_cluster_reads_batched",
            "rtl_reads_upload", "rtl_cluster_resident", "rtl_set_shard", "rtl_extract_kmers", "rtl_bv_scan",
            "rtl_pair_similarity", "rtl_poa_msa", "rtl_correct_reads", "rtl_set_labels", "rtl_set_cluster_ids", "rtl_hps_encode", "rtl_hps_decode"]
 
@@ -71,6 +72,9 @@ def load_library():
     L.rtl_cluster_reads.restype = c_i
     L.rtl_cluster_reads.argtypes = [c_p, c_p, c_p, c_u32, c_i, c_d, c_d, c_d, c_d, c_d, c_d, c_i, c_p, c_p, c_p, c_p,
                                     c_p, c_p]
+    L.rtl_cluster_reads_batched.restype = c_i
+    L.rtl_cluster_reads_batched.argtypes = [c_p, c_p, c_p, c_u32, c_p, c_u32, c_i, c_d, c_d, c_d, c_d, c_d, c_d, c_i, c_p, c_p,
+                                            c_p, c_p, c_p, c_p, c_p]
     L.rtl_reads_upload.restype = c_i
     L.rtl_reads_upload.argtypes = [c_p, c_p, c_p, c_u32]
     L.rtl_cluster_resident.restype = c_i
@@ -220,6 +224,24 @@ class Context:
                                              min_bv_threshold, bv_falloff, repr_percentile, int(is_rna),
                                              *[_ptr(a) for a in out], ctypes.byref(nc)))
         return self._pack(nc.value, out)
+
+    def cluster_reads_batched(self, bases, offsets, seg_off, kmer_size=10, t_s=0.2, t_v=1e6, bv_threshold=0.4,
+                              min_bv_threshold=0.2, bv_falloff=0.05, repr_percentile=0.15, is_rna=False):
+        """n_seg independent cluster_reads problems in one pass (the per-gene loop of `rattle cluster --iso`,
+        main.cpp:281-324): reads seg_off[s]:seg_off[s+1] are segment s.  Returns (ClusterSet, seg_cl_off): the clusters
+        of segment s are seg_cl_off[s]:seg_cl_off[s+1], their ids count from the segment's first read."""
+        bases = _bases(bases)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.uint32)
+        n = len(offsets) - 1
+        n_seg = len(seg_off) - 1
+        out = self._cluster_out(n)
+        seg_cl_off = np.zeros(n_seg + 1, dtype=np.int64)
+        nc = ctypes.c_int32(0)
+        self._check(self.L.rtl_cluster_reads_batched(self.h, _ptr(bases), _ptr(offsets), n, _ptr(seg_off), n_seg, kmer_size,
+                                                     t_s, t_v, bv_threshold, min_bv_threshold, bv_falloff, repr_percentile,
+                                                     int(is_rna), *[_ptr(a) for a in out], ctypes.byref(nc), _ptr(seg_cl_off)))
+        return self._pack(nc.value, out), seg_cl_off
 
     def upload(self, bases, offsets):
         bases = _bases(bases)

@@ -9,7 +9,8 @@ void cluster_upload(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, ui
 void cluster_extract(rtl_ctx *ctx, int k, int both);
 void cluster_run(rtl_ctx *ctx, int k, double t_s, double t_v, double bv_thr, double bv_min, double bv_falloff,
                  double repr_pct, int is_rna, int32_t *main_id, uint8_t *main_rev, int64_t *cl_off, int32_t *mem_id,
-                 uint8_t *mem_rev, int32_t *n_clusters);
+                 uint8_t *mem_rev, int32_t *n_clusters, const uint32_t *seg_off = nullptr, uint32_t n_seg = 0,
+                 int64_t *seg_cl_off = nullptr);
 void cluster_download_kmers(rtl_ctx *ctx, uint32_t *fh, int32_t *fp, uint32_t *rh, int32_t *rp, uint64_t *bf,
                             uint64_t *br);
 void cluster_bv_scan_dense(rtl_ctx *ctx, int k, int is_rna, const int32_t *seed_reads, int n_seeds,
@@ -209,6 +210,29 @@ int rtl_cluster_reads(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, 
         cluster_upload(ctx, bases, offsets, n_reads);
         cluster_run(ctx, kmer_size, t_s, t_v, bv_threshold, min_bv_threshold, bv_falloff, repr_percentile, is_rna,
                     main_id, main_rev, cl_off, mem_id, mem_rev, n_clusters);
+        ctx->stats.total_ms = now_ms() - t0;
+        return RTL_OK;
+    });
+}
+
+int rtl_cluster_reads_batched(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, uint32_t n_reads,
+                              const uint32_t *seg_off, uint32_t n_seg, int kmer_size, double t_s, double t_v,
+                              double bv_threshold, double min_bv_threshold, double bv_falloff, double repr_percentile,
+                              int is_rna, int32_t *main_id, uint8_t *main_rev, int64_t *cl_off, int32_t *mem_id,
+                              uint8_t *mem_rev, int32_t *n_clusters, int64_t *seg_cl_off) {
+    return guarded(ctx, [&]() {
+        ctx->stats = rtl_stats{};
+        if (!seg_off || !seg_cl_off || !n_clusters || !cl_off) throw InputError("null segment / output buffers");
+        if (n_reads == 0) {  // every segment is an empty read set: empty cluster sets (cluster.cpp:93-259 with no reads)
+            *n_clusters = 0;
+            cl_off[0] = 0;
+            for (uint32_t s = 0; s <= n_seg; ++s) seg_cl_off[s] = 0;
+            return RTL_OK;
+        }
+        const double t0 = now_ms();
+        cluster_upload(ctx, bases, offsets, n_reads);
+        cluster_run(ctx, kmer_size, t_s, t_v, bv_threshold, min_bv_threshold, bv_falloff, repr_percentile, is_rna,
+                    main_id, main_rev, cl_off, mem_id, mem_rev, n_clusters, seg_off, n_seg, seg_cl_off);
         ctx->stats.total_ms = now_ms() - t0;
         return RTL_OK;
     });

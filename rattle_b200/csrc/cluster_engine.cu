@@ -72,7 +72,7 @@ struct ClusterState {
     DevBuf<uint64_t> long_off, long_scratch;
     // wave state
     DevBuf<uint8_t> taken, owner_rev, is_seed;
-    DevBuf<int32_t> owner, item_read, item_rid, cand, seed_item, wave, shard_list;
+    DevBuf<int32_t> owner, item_read, item_rid, item_seg, cand, seed_item, wave, shard_list;
     DevBuf<uint32_t> memo;      // known k-mer-test failures between representatives (cluster_kernels.cuh: Memo)
     uint32_t rid_dim = 0;       // 0 = memo off
     DevBuf<uint32_t> best, acc;
@@ -102,7 +102,8 @@ static void set_smem_attrs(ClusterState &S) {
     if (S.smem_attr_set) return;
     const int max_smem = 227 * 1024;
     CK(cudaFuncSetAttribute(k_extract_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CK(cudaFuncSetAttribute(k_bv_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    // (k_bv_scan also holds a statically allocated mbarrier: its dynamic limit is what a full seed tile needs)
+    CK(cudaFuncSetAttribute(k_bv_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, BVS_TS * (64 * 8 + 8)));
     CK(cudaFuncSetAttribute(k_bv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CK(cudaFuncSetAttribute(k_join_count, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CK(cudaFuncSetAttribute(k_pair_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -360,9 +361,14 @@ static void ensure_work_buffers(rtl_ctx *ctx, ClusterState &S, int64_t M) {
 
 // One greedy pass (cluster.cpp:124-166 with items = reads, :174-245 with items = cluster representatives).
 // Result: owner[j] = item index of the seed that took item j (owner[j]==j for seeds), owner_rev[j] = rev flag.
+// Batched clustering (h_item_seg != nullptr): the items are the concatenation of independent problems ("segments",
+// contiguous item ranges; main.cpp:281-324 clusters every gene's reads on their own).  Pairs only exist inside a segment
+// (the scan drops the others), so one pass over all items is every segment's greedy pass at once; phase B of a wave
+// only has to reach the end of the segment its last candidate lies in (h_item_seg_end[item] = first item behind it).
 static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const int32_t *h_item_rid, double thr, bool both,
                         double t_s, double t_v,
-                        std::vector<int32_t> &owner, std::vector<uint8_t> &owner_rev) {
+                        std::vector<int32_t> &owner, std::vector<uint8_t> &owner_rev,
+                        const int32_t *h_item_seg = nullptr, const int32_t *h_item_seg_end = nullptr) {
     ClusterState &S = state(ctx);
     cudaStream_t st = ctx->stream;
     const int W = ctx->wave;
@@ -381,6 +387,12 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
         memo.item_rid = S.item_rid.p;
         memo.bits = S.memo.p;
         memo.rid_dim = S.rid_dim;
+    }
+    const int32_t *d_item_seg = nullptr;
+    if (h_item_seg) {
+        CK(cudaMemcpyAsync(S.item_seg.need(M), h_item_seg, (size_t)M * 4, cudaMemcpyHostToDevice, st));
+        ctx->stats.h2d_bytes += (int64_t)M * 4;
+        d_item_seg = S.item_seg.p;
     }
     // multi-GPU: this rank's targets as a compact ascending list (key = the representative's compact id in the merge
     // rounds, so that a rank meets the pairs it has memoised again; the item index otherwise) — phase B then walks only
@@ -417,6 +429,13 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
         CK(cudaMemsetAsync(S.acc.p, 0xff, (size_t)W * W * 4, st));
         CK(cudaMemsetAsync(S.counters.p, 0, 3 * sizeof(unsigned long long), st));
         ctx->stats.kernel_launches += 2;
+        // batched: how far does phase B have to look?  (the cursor now stands behind the last candidate)
+        int b_hi = M;
+        if (h_item_seg_end) {
+            CK(cudaMemcpyAsync(hw, S.wave.p, 12, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (hw[1] >= W && hw[0] >= 1 && hw[0] <= M) b_hi = h_item_seg_end[hw[0] - 1];
+        }
         // ---- phase A: candidates x candidates
         {
             BvScanArgs a{};
@@ -425,6 +444,7 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
             a.bv_stride = S.bv_stride;
             a.pc = S.pc.p;
             a.item_read = d_item_read;
+            a.item_seg = d_item_seg;
             a.seed_item = S.cand.p;
             a.n_seeds_p = S.wave.p + 1;
             a.tgt_list = S.cand.p;
@@ -466,7 +486,7 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
         // target space: items [b_lo, M), or — sharded — the entries of this rank's list from the first one >= b_lo
         const bool sharded = ctx->world > 1;
         const int64_t x_lo = sharded ? (int64_t)(std::lower_bound(shard.begin(), shard.end(), b_lo) - shard.begin()) : b_lo;
-        const int64_t x_hi = sharded ? (int64_t)shard.size() : M;
+        const int64_t x_hi = sharded ? (int64_t)shard.size() : b_hi;
         for (int64_t c0 = x_lo; c0 < x_hi; c0 += chunk) {
             const int64_t c1 = std::min<int64_t>(x_hi, c0 + chunk);
             CK(cudaMemsetAsync(S.counters.p, 0, 3 * sizeof(unsigned long long), st));
@@ -476,6 +496,7 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
             a.bv_stride = S.bv_stride;
             a.pc = S.pc.p;
             a.item_read = d_item_read;
+            a.item_seg = d_item_seg;
             a.seed_item = S.seed_item.p;
             a.n_seeds_p = S.wave.p + 2;
             a.tgt_list = sharded ? S.shard_list.p + c0 : nullptr;
@@ -514,7 +535,8 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
                     throw CudaError("allreduce callback failed");
                 CK(cudaMemcpyAsync(hw + 3, S.best.p + M, 4, cudaMemcpyDeviceToHost, st));  // wave[3] is unused by the host
             }
-            k_apply<<<ctx->n_sm, 256, 0, st>>>(S.best.p, b_lo, M, S.seed_item.p, S.taken.p, S.owner.p, S.owner_rev.p);
+            k_apply<<<ctx->n_sm, 256, 0, st>>>(S.best.p, b_lo, sharded ? M : b_hi, S.seed_item.p, S.taken.p, S.owner.p,
+                                               S.owner_rev.p);
             ctx->stats.kernel_launches++;
         }
         CK(cudaMemcpyAsync(hw, S.wave.p, 12, cudaMemcpyDeviceToHost, st));
@@ -568,9 +590,32 @@ static Member pick_main(std::vector<Member> &m, const std::vector<int32_t> &len,
 
 void cluster_run(rtl_ctx *ctx, int k, double t_s, double t_v, double bv_thr, double bv_min, double bv_falloff,
                  double repr_pct, int is_rna, int32_t *main_id, uint8_t *main_rev, int64_t *cl_off, int32_t *mem_id,
-                 uint8_t *mem_rev, int32_t *n_clusters) {
+                 uint8_t *mem_rev, int32_t *n_clusters, const uint32_t *seg_off, uint32_t n_seg, int64_t *seg_cl_off) {
     ClusterState &S = state(ctx);
     const double t_begin = now_ms();
+    // batched clustering: reads [seg_off[s], seg_off[s+1]) are segment s, an independent cluster_reads problem whose
+    // seq_ids count from the segment's first read; every segment's clusters come out together, in segment order
+    const bool batched = seg_off != nullptr;
+    std::vector<int32_t> read_seg, read_seg_end;
+    if (batched) {
+        if (n_seg == 0 || seg_off[0] != 0 || seg_off[n_seg] != S.n || !seg_cl_off) throw InputError("bad segment offsets");
+        read_seg.resize(S.n);
+        read_seg_end.resize(S.n);
+        for (uint32_t s = 0; s < n_seg; ++s) {
+            if (seg_off[s + 1] < seg_off[s] || seg_off[s + 1] > S.n) throw InputError("segment offsets are not monotonic");
+            for (uint32_t i = seg_off[s]; i < seg_off[s + 1]; ++i) {
+                read_seg[i] = (int32_t)s;
+                read_seg_end[i] = (int32_t)seg_off[s + 1];
+            }
+        }
+    }
+    // (segments are bin-packed over GPUs by the caller, SURVEY.md 8e: no pair sharding inside a batched call)
+    struct WorldGuard {
+        rtl_ctx *c;
+        int w;
+        ~WorldGuard() { c->world = w; }
+    } world_guard{ctx, ctx->world};
+    if (batched) ctx->world = 1;
     const bool both = !is_rna;
     for (int c = 0; c < 4; ++c) S.ev.acc[c] = 0;
     S.ex_k = -1;  // one call = the whole hot path: extraction is never reused across cluster_reads calls
@@ -581,7 +626,8 @@ void cluster_run(rtl_ctx *ctx, int k, double t_s, double t_v, double bv_thr, dou
 
     std::vector<int32_t> owner;
     std::vector<uint8_t> orev;
-    greedy_pass(ctx, N, nullptr, nullptr, bv_thr, both, t_s, t_v, owner, orev);
+    greedy_pass(ctx, N, nullptr, nullptr, bv_thr, both, t_s, t_v, owner, orev, batched ? read_seg.data() : nullptr,
+                batched ? read_seg_end.data() : nullptr);
 
     std::vector<Cluster> cl;
     {
@@ -599,7 +645,7 @@ void cluster_run(rtl_ctx *ctx, int k, double t_s, double t_v, double bv_thr, dou
 
     double thr = bv_thr - bv_falloff;
     bool last = false;
-    std::vector<int32_t> rep, rep_rid;
+    std::vector<int32_t> rep, rep_rid, item_seg, item_seg_end;
     // Memo of failed k-mer tests between representatives (cluster_kernels.cuh: Memo).  A read gets a compact id when
     // it first becomes a representative; only clusters that absorbed others can change theirs, so there are fewer
     // than 2 x (clusters after the initial pass) ids in total.
@@ -623,7 +669,18 @@ void cluster_run(rtl_ctx *ctx, int k, double t_s, double t_v, double bv_thr, dou
             if (read_rid[rep[i]] < 0) read_rid[rep[i]] = next_rid++;
             rep_rid[i] = read_rid[rep[i]];
         }
-        greedy_pass(ctx, M, rep.data(), rep_rid.data(), thr, both, t_s, t_v, owner, orev);
+        if (batched) {  // clusters stay grouped by segment: seeds are met in item order
+            item_seg.resize(M);
+            item_seg_end.resize(M);
+            for (int i = 0; i < M; ++i) item_seg[i] = read_seg[rep[i]];
+            for (int i = M - 1, end = M; i >= 0; --i) {
+                if (i + 1 < M && item_seg[i + 1] != item_seg[i]) end = i + 1;
+                if (i + 1 < M && item_seg[i + 1] < item_seg[i]) throw StateError("batched clustering: clusters left segment order");
+                item_seg_end[i] = end;
+            }
+        }
+        greedy_pass(ctx, M, rep.data(), rep_rid.data(), thr, both, t_s, t_v, owner, orev, batched ? item_seg.data() : nullptr,
+                    batched ? item_seg_end.data() : nullptr);
         std::vector<Cluster> next;
         std::vector<int32_t> slot(M, -1);
         for (int i = 0; i < M; ++i)
@@ -651,17 +708,27 @@ void cluster_run(rtl_ctx *ctx, int k, double t_s, double t_v, double bv_thr, dou
     }
 
     int64_t o = 0;
+    uint32_t seg_at = 0;  // batched: next segment whose first cluster has not been seen
     for (size_t c = 0; c < cl.size(); ++c) {
-        main_id[c] = cl[c].main.id;
+        int32_t base = 0;
+        if (batched) {
+            const uint32_t sg = (uint32_t)read_seg[cl[c].main.id];
+            if (sg + 1 < seg_at) throw StateError("batched clustering: clusters left segment order");
+            while (seg_at <= sg) seg_cl_off[seg_at++] = (int64_t)c;
+            base = (int32_t)seg_off[sg];
+        }
+        main_id[c] = cl[c].main.id - base;
         main_rev[c] = cl[c].main.rev;
         cl_off[c] = o;
         for (auto &m : cl[c].mem) {
-            mem_id[o] = m.id;
+            mem_id[o] = m.id - base;
             mem_rev[o] = m.rev;
             ++o;
         }
     }
     cl_off[cl.size()] = o;
+    if (batched)
+        while (seg_at <= n_seg) seg_cl_off[seg_at++] = (int64_t)cl.size();
     *n_clusters = (int32_t)cl.size();
     ctx->stats.bv_pairs += (int64_t)S.h_counters.p[3];  // device counters are cumulative over the passes
     ctx->stats.full_pairs += (int64_t)S.h_counters.p[4];

@@ -261,6 +261,7 @@ struct BvScanArgs {
     int bv_stride;             // uint64 words between consecutive reads' bitvectors (128: [fwd 64 | rev 64] per read)
     const int32_t *pc;
     const int32_t *item_read;  // nullable
+    const int32_t *item_seg;   // nullable: segment of every item (batched clustering: only pairs inside a segment exist)
     const int32_t *seed_item;  // n_seeds (device count in *n_seeds_p)
     const int32_t *n_seeds_p;
     const int32_t *tgt_list;   // nullable: explicit target items
@@ -428,6 +429,7 @@ __global__ void __launch_bounds__(BVS_THREADS) k_bv_scan(BvScanArgs A) {
             const int s = g + sub;
             bool valid = cur.live && sub < lim;
             if (valid && A.order_check) valid = sitem[s] < item;
+            if (valid && A.item_seg) valid = A.item_seg[sitem[s]] == A.item_seg[item];
             const uint32_t cf = mine & 0xffffu, cr = mine >> 16;
             bool pf = false, pr = false;
             if (valid) {
@@ -635,6 +637,7 @@ __global__ void __launch_bounds__(BVT_THREADS, 3) k_bv_stream(BvScanArgs A) {
                 const int s = g + j;
                 bool valid = live && j < lim;
                 if (valid && A.order_check) valid = sitem[s] < item;
+                if (valid && A.item_seg) valid = A.item_seg[sitem[s]] == A.item_seg[item];
                 const uint32_t cf = mine & 0xffffu, cr = mine >> 16;
                 bool pf = false, pr = false;
                 if (valid) {

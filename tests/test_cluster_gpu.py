@@ -309,3 +309,56 @@ def test_bulk_copy_ring_scan_matches_numpy_and_clusters(ctx, orc):
     finally:
         ctx.set_option("wave", 512)
         ctx.set_option("bv_kernel", 0)
+
+
+def _iso_segments(rs, gene_cl):
+    """the per-gene read sets of `rattle cluster --iso` (main.cpp:281-298): members by id descending, then stably by
+    length descending"""
+    lens = rs.lengths()
+    segs = []
+    for c in range(gene_cl.n_clusters):
+        mem = np.asarray(gene_cl.mem_id[gene_cl.cl_off[c]:gene_cl.cl_off[c + 1]], dtype=np.int64)
+        mem = np.sort(mem)[::-1]
+        segs.append(mem[np.argsort(-lens[mem], kind="stable")])
+    return segs
+
+
+@pytest.mark.parametrize("wave", [512, 16])
+def test_cluster_reads_batched_equals_per_gene_calls(ctx, orc, wave):
+    """rtl_cluster_reads_batched (one pass over every gene's reads, main.cpp:281-324) == one cluster_reads per gene,
+    on the GPU and in the oracle; small wave: candidates of one wave lie in one segment, large: they span many"""
+    rs = synth.generate(seed=17, n_genes=30, n_isoforms=2, reads_per_tx=9, len_mean=900.0).sorted_by_length()[0]
+    gene_cl = ctx.cluster_reads(rs.bases, rs.offsets, is_rna=False)
+    segs = _iso_segments(rs, gene_cl)
+    segs.insert(3, np.zeros(0, dtype=np.int64))  # an empty segment is an empty read set
+    order = np.concatenate(segs)
+    sub = rs.take(order)
+    seg_off = np.concatenate([[0], np.cumsum([len(s) for s in segs])]).astype(np.uint32)
+    kw = dict(kmer_size=11, t_s=0.3, t_v=25.0)  # --iso-kmer-size / --iso-score-threshold / --iso-max-variance defaults
+    ctx.set_option("wave", wave)
+    try:
+        got, seg_cl_off = ctx.cluster_reads_batched(sub.bases, sub.offsets, seg_off, is_rna=False, **kw)
+    finally:
+        ctx.set_option("wave", 512)
+    assert seg_cl_off[0] == 0 and seg_cl_off[-1] == got.n_clusters
+    n_iso = 0
+    for s, ids in enumerate(segs):
+        c0, c1 = int(seg_cl_off[s]), int(seg_cl_off[s + 1])
+        if len(ids) == 0:
+            assert c0 == c1
+            continue
+        one = rs.take(ids)
+        exp = orc.cluster_reads(one.bases, one.offsets, k=11, t_s=0.3, t_v=25.0, is_rna=False, n_threads=4)
+        assert c1 - c0 == exp["n_clusters"], s
+        assert np.array_equal(got.main_id[c0:c1], exp["main_id"]) and np.array_equal(got.main_rev[c0:c1], exp["main_rev"]), s
+        m0, m1 = int(got.cl_off[c0]), int(got.cl_off[c1])
+        assert np.array_equal(got.cl_off[c0:c1 + 1] - m0, exp["cl_off"]), s
+        assert np.array_equal(got.mem_id[m0:m1], exp["mem_id"]) and np.array_equal(got.mem_rev[m0:m1], exp["mem_rev"]), s
+        n_iso += c1 - c0
+    assert n_iso > gene_cl.n_clusters  # the isoform level splits genes
+    # and the per-gene GPU calls give the same
+    for s in (0, 5, len(segs) - 1):
+        one = rs.take(segs[s])
+        single = ctx.cluster_reads(one.bases, one.offsets, is_rna=False, **kw)
+        c0, c1 = int(seg_cl_off[s]), int(seg_cl_off[s + 1])
+        assert single.n_clusters == c1 - c0 and np.array_equal(single.main_id, got.main_id[c0:c1])
