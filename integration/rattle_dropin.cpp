@@ -9,12 +9,22 @@
 // (-I$(REF), nothing is copied) and linked with the reference's unmodified main.cpp / fasta.cpp / utils.cpp INSTEAD OF
 // cluster.cpp, kmer.cpp, similarity.cpp, correct.cpp and spoa (integration/Makefile).  The result is the `rattle`
 // CLI with `cluster`, `correct` and `polish` running on the GPU: same arguments, same clusters.out / *.fq bytes.
+//
+// `rattle cluster --iso` (main.cpp:281-324) calls cluster_reads once per gene cluster, thousands of small calls.  main.cpp
+// stays unmodified, so the batching happens behind the signature: the gene-level call remembers its reads and result;
+// when the next call's read set is exactly what main.cpp:283-296 builds for gene cluster 0, ALL genes' read sets are
+// clustered in one rtl_cluster_reads_batched pass with that call's parameters, and the following calls are answered from
+// the cache after their read set has been compared with the prediction (any mismatch drops the cache and clusters
+// directly).  RATTLE_B200_DEVICES=0,1,... spreads the genes (independent problems) and the clusters of
+// `correct` (independent packs) over several GPUs from this one process; RATTLE_B200_TRACE=1 reports what ran.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "cluster.hpp"
@@ -25,21 +35,37 @@
 
 namespace {
 
-rtl_ctx *context() {
-    static rtl_ctx *ctx = nullptr;
-    if (!ctx) {
-        const char *dev = getenv("RATTLE_B200_DEVICE");
-        if (rtl_init(dev ? atoi(dev) : 0, &ctx) != RTL_OK) {
-            fprintf(stderr, "rattle_b200: %s\n", rtl_last_error(nullptr));
-            exit(EXIT_FAILURE);  // no CPU fallback
+// one context per GPU of RATTLE_B200_DEVICES (default: RATTLE_B200_DEVICE or device 0)
+std::vector<rtl_ctx *> &contexts() {
+    static std::vector<rtl_ctx *> ctxs;
+    if (ctxs.empty()) {
+        std::vector<int> devs;
+        if (const char *list = getenv("RATTLE_B200_DEVICES")) {
+            std::stringstream ss(list);
+            std::string tok;
+            while (getline(ss, tok, ',')) devs.push_back(atoi(tok.c_str()));
+        }
+        if (devs.empty()) {
+            const char *dev = getenv("RATTLE_B200_DEVICE");
+            devs.push_back(dev ? atoi(dev) : 0);
+        }
+        for (int d : devs) {
+            rtl_ctx *c = nullptr;
+            if (rtl_init(d, &c) != RTL_OK) {
+                fprintf(stderr, "rattle_b200: device %d: %s\n", d, rtl_last_error(nullptr));
+                exit(EXIT_FAILURE);  // no CPU fallback
+            }
+            ctxs.push_back(c);
         }
     }
-    return ctx;
+    return ctxs;
 }
+rtl_ctx *context() { return contexts()[0]; }
+bool trace() { return getenv("RATTLE_B200_TRACE") != nullptr; }
 
-void check(int rc, const char *what) {
+void check(int rc, const char *what, rtl_ctx *ctx = nullptr) {
     if (rc < 0) {
-        fprintf(stderr, "rattle_b200: %s failed: %s\n", what, rtl_last_error(context()));
+        fprintf(stderr, "rattle_b200: %s failed: %s\n", what, rtl_last_error(ctx ? ctx : context()));
         exit(EXIT_FAILURE);
     }
 }
@@ -110,30 +136,171 @@ std::vector<std::string> splitString(std::string str, char delimiter) {
     return out;
 }
 
+namespace {
+
+struct ClusterParams {
+    int k;
+    double t_s, t_v, bv, bv_min, bv_falloff, pct;
+    bool is_rna;
+    bool operator==(const ClusterParams &o) const {
+        return k == o.k && t_s == o.t_s && t_v == o.t_v && bv == o.bv && bv_min == o.bv_min && bv_falloff == o.bv_falloff &&
+               pct == o.pct && is_rna == o.is_rna;
+    }
+};
+
+cluster_set_t to_cluster_set(const int32_t *main_id, const uint8_t *main_rev, const int64_t *cl_off, const int32_t *mem_id,
+                             const uint8_t *mem_rev, int64_t c0, int64_t c1) {
+    cluster_set_t result((size_t)(c1 - c0));
+    for (int64_t c = c0; c < c1; ++c) {
+        cluster_t &cl = result[(size_t)(c - c0)];
+        cl.main_seq = cseq_t{main_id[c], main_rev[c] != 0};
+        cl.seqs.reserve((size_t)(cl_off[c + 1] - cl_off[c]));
+        for (int64_t i = cl_off[c]; i < cl_off[c + 1]; ++i) cl.seqs.push_back(cseq_t{mem_id[i], mem_rev[i] != 0});
+    }
+    return result;
+}
+
+cluster_set_t cluster_direct(const FlatReads &f, uint32_t n, const ClusterParams &p) {
+    std::vector<int32_t> main_id(n), mem_id(n);
+    std::vector<uint8_t> main_rev(n), mem_rev(n);
+    std::vector<int64_t> cl_off((size_t)n + 1);
+    int32_t n_clusters = 0;
+    check(rtl_cluster_reads(context(), f.bases.data(), f.off.data(), n, p.k, p.t_s, p.t_v, p.bv, p.bv_min, p.bv_falloff, p.pct,
+                            p.is_rna ? 1 : 0, main_id.data(), main_rev.data(), cl_off.data(), mem_id.data(), mem_rev.data(),
+                            &n_clusters),
+          "rtl_cluster_reads");
+    return to_cluster_set(main_id.data(), main_rev.data(), cl_off.data(), mem_id.data(), mem_rev.data(), 0, n_clusters);
+}
+
+// What the last direct ("gene-level") call saw and returned, and — once the per-gene loop of main.cpp:281-324 has been
+// recognised — every gene's isoform-level cluster set.
+struct IsoCache {
+    bool armed = false;              // a gene-level result is remembered
+    FlatReads reads;                 // its read set
+    std::vector<std::vector<int32_t>> gene_reads;  // per gene cluster: the read ids main.cpp:283-296 will pass, in order
+    size_t next = 0;                 // gene cluster the next call should be about
+    bool have = false;               // batched results below are valid for `params`
+    ClusterParams params{};
+    std::vector<cluster_set_t> result;
+    void drop() {
+        armed = have = false;
+        reads = FlatReads();
+        gene_reads.clear();
+        result.clear();
+        next = 0;
+    }
+} g_iso;
+
+// main.cpp:283-296: members by seq_id descending, then stably by read length descending
+void arm_iso_cache(const FlatReads &f, const cluster_set_t &genes) {
+    g_iso.drop();
+    if (genes.size() < 2) return;  // nothing to batch
+    g_iso.reads = f;
+    g_iso.gene_reads.resize(genes.size());
+    for (size_t g = 0; g < genes.size(); ++g) {
+        std::vector<int32_t> &ids = g_iso.gene_reads[g];
+        for (const auto &cs : genes[g].seqs) ids.push_back(cs.seq_id);
+        std::stable_sort(ids.begin(), ids.end(), [](int32_t a, int32_t b) { return a > b; });
+        std::stable_sort(ids.begin(), ids.end(), [&f](int32_t a, int32_t b) {
+            return f.off[a + 1] - f.off[a] > f.off[b + 1] - f.off[b];
+        });
+    }
+    g_iso.armed = true;
+}
+
+bool matches_prediction(const read_set_t &reads, size_t g) {
+    if (!g_iso.armed || g >= g_iso.gene_reads.size()) return false;
+    const std::vector<int32_t> &ids = g_iso.gene_reads[g];
+    if (ids.size() != reads.size()) return false;
+    for (size_t j = 0; j < ids.size(); ++j) {
+        const uint64_t a = g_iso.reads.off[ids[j]], b = g_iso.reads.off[ids[j] + 1];
+        if (reads[j].seq.size() != b - a || memcmp(reads[j].seq.data(), g_iso.reads.bases.data() + a, b - a) != 0) return false;
+    }
+    return true;
+}
+
+// all genes' isoform-level clusterings: genes are dealt to the GPUs largest first (by sum of members squared), every GPU
+// runs ONE batched call over its genes
+void run_iso_batched(const ClusterParams &p) {
+    const size_t G = g_iso.gene_reads.size();
+    std::vector<rtl_ctx *> &ctxs = contexts();
+    const size_t D = ctxs.size();
+    std::vector<size_t> order(G);
+    for (size_t g = 0; g < G; ++g) order[g] = g;
+    std::stable_sort(order.begin(), order.end(),
+                     [](size_t a, size_t b) { return g_iso.gene_reads[a].size() > g_iso.gene_reads[b].size(); });
+    std::vector<std::vector<size_t>> mine(D);
+    std::vector<double> load(D, 0.0);
+    for (size_t g : order) {
+        const size_t d = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
+        mine[d].push_back(g);
+        const double m = (double)g_iso.gene_reads[g].size();
+        load[d] += m * m + 1.0;
+    }
+    g_iso.result.assign(G, cluster_set_t());
+    auto work = [&](size_t d) {
+        std::vector<size_t> &genes = mine[d];
+        std::sort(genes.begin(), genes.end());
+        if (genes.empty()) return;
+        std::string bases;
+        std::vector<uint64_t> off{0};
+        std::vector<uint32_t> seg_off{0};
+        for (size_t g : genes) {
+            for (int32_t id : g_iso.gene_reads[g]) {
+                bases.append(g_iso.reads.bases, g_iso.reads.off[id], g_iso.reads.off[id + 1] - g_iso.reads.off[id]);
+                off.push_back(bases.size());
+            }
+            seg_off.push_back((uint32_t)(off.size() - 1));
+        }
+        const uint32_t n = (uint32_t)(off.size() - 1);
+        std::vector<int32_t> main_id(n), mem_id(n);
+        std::vector<uint8_t> main_rev(n), mem_rev(n);
+        std::vector<int64_t> cl_off((size_t)n + 1), seg_cl_off(genes.size() + 1);
+        int32_t n_clusters = 0;
+        check(rtl_cluster_reads_batched(ctxs[d], bases.data(), off.data(), n, seg_off.data(), (uint32_t)genes.size(), p.k,
+                                        p.t_s, p.t_v, p.bv, p.bv_min, p.bv_falloff, p.pct, p.is_rna ? 1 : 0, main_id.data(),
+                                        main_rev.data(), cl_off.data(), mem_id.data(), mem_rev.data(), &n_clusters,
+                                        seg_cl_off.data()),
+              "rtl_cluster_reads_batched", ctxs[d]);
+        for (size_t i = 0; i < genes.size(); ++i)
+            g_iso.result[genes[i]] = to_cluster_set(main_id.data(), main_rev.data(), cl_off.data(), mem_id.data(),
+                                                    mem_rev.data(), seg_cl_off[i], seg_cl_off[i + 1]);
+        if (trace())
+            fprintf(stderr, "rattle_b200: device slot %zu: %zu gene clusters (%u reads) -> %d isoform clusters in one batched pass\n",
+                    d, genes.size(), n, n_clusters);
+    };
+    std::vector<std::thread> th;
+    for (size_t d = 1; d < D; ++d) th.emplace_back(work, d);
+    work(0);
+    for (auto &t : th) t.join();
+    g_iso.params = p;
+    g_iso.have = true;
+}
+
+}  // namespace
+
 // cluster.hpp:44.  min_reads_cluster and use_hc are ignored by the reference as well (cluster.cpp:93-259 never reads
 // the former; main.cpp always passes use_hc=false); n_threads and verbose only affect the CPU build.
 cluster_set_t cluster_reads(const read_set_t &reads, int kmer_size, double t_s, double t_v, double bv_threshold,
                             double min_bv_threshold, double bv_falloff, int /*min_reads_cluster*/, bool /*use_hc*/,
                             double repr_percentile, bool is_rna, bool /*verbose*/, int /*n_threads*/) {
-    cluster_set_t result;
     const uint32_t n = (uint32_t)reads.size();
-    if (n == 0) return result;
-    const FlatReads f = flatten(reads, false);
-    std::vector<int32_t> main_id(n), mem_id(n);
-    std::vector<uint8_t> main_rev(n), mem_rev(n);
-    std::vector<int64_t> cl_off((size_t)n + 1);
-    int32_t n_clusters = 0;
-    check(rtl_cluster_reads(context(), f.bases.data(), f.off.data(), n, kmer_size, t_s, t_v, bv_threshold,
-                            min_bv_threshold, bv_falloff, repr_percentile, is_rna ? 1 : 0, main_id.data(), main_rev.data(),
-                            cl_off.data(), mem_id.data(), mem_rev.data(), &n_clusters),
-          "rtl_cluster_reads");
-    result.resize(n_clusters);
-    for (int c = 0; c < n_clusters; ++c) {
-        cluster_t &cl = result[c];
-        cl.main_seq = cseq_t{main_id[c], main_rev[c] != 0};
-        cl.seqs.reserve((size_t)(cl_off[c + 1] - cl_off[c]));
-        for (int64_t i = cl_off[c]; i < cl_off[c + 1]; ++i) cl.seqs.push_back(cseq_t{mem_id[i], mem_rev[i] != 0});
+    if (n == 0) return cluster_set_t();
+    const ClusterParams p{kmer_size, t_s, t_v, bv_threshold, min_bv_threshold, bv_falloff, repr_percentile, is_rna};
+    // the per-gene loop of `cluster --iso`: answered from one batched pass over all genes
+    if (g_iso.armed && getenv("RATTLE_B200_NO_ISO_BATCH") == nullptr) {
+        if (matches_prediction(reads, g_iso.next) && (!g_iso.have || g_iso.params == p)) {
+            if (!g_iso.have) run_iso_batched(p);
+            cluster_set_t out = std::move(g_iso.result[g_iso.next]);
+            if (++g_iso.next == g_iso.gene_reads.size()) g_iso.drop();
+            return out;
+        }
+        if (trace()) fprintf(stderr, "rattle_b200: call does not continue the per-gene loop: clustering directly\n");
+        g_iso.drop();
     }
+    const FlatReads f = flatten(reads, false);
+    cluster_set_t result = cluster_direct(f, n, p);
+    arm_iso_cache(f, result);
     return result;
 }
 
@@ -165,20 +332,87 @@ correction_results_t correct_reads(const cluster_set_t &clusters, read_set_t &re
     }
     std::vector<const char *> lab;
     for (const auto &l : labels) lab.push_back(l.c_str());
-    check(rtl_set_labels(context(), lab.data(), (int)lab.size()), "rtl_set_labels");
-    // generous first guess (corrected reads are about as long as the raw ones), exact sizes on RTL_ERR_CAPACITY
-    std::unique_ptr<char[]> out[3];  // uninitialised: untouched pages cost nothing
-    const int64_t guess = 3 * (int64_t)f.bases.size() + (int64_t)f.headers.size() + 64 * (int64_t)(reads.size() + nc) + 1024;
-    int64_t len[3] = {guess, guess, guess};
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        for (int i = 0; i < 3; ++i) out[i].reset(new char[(size_t)len[i] + 1]);
-        const int rc = rtl_correct_reads(context(), f.bases.data(), f.quals.data(), f.off.data(), (uint32_t)reads.size(),
-                                         f.headers.data(), f.hoff.data(), main_id.data(), main_rev.data(), main_gene.data(),
-                                         cl_off.data(), mem_id.data(), mem_rev.data(), mem_gene.data(), nc, min_occ, gap_occ,
-                                         err_ratio, split, min_reads, out[0].get(), &len[0], out[1].get(), &len[1],
-                                         out[2].get(), &len[2]);
-        if (rc == RTL_OK) break;
-        if (rc != RTL_ERR_CAPACITY || attempt == 1) check(rc, "rtl_correct_reads");
+    // clusters are independent: device d corrects clusters d, d+D, d+2D, ... and is told their ids in the
+    // whole set (rtl_set_cluster_ids), which is what the headers carry
+    std::vector<rtl_ctx *> &ctxs = contexts();
+    const int D = (int)std::min<size_t>(ctxs.size(), (size_t)std::max(nc, 1));
+    struct Part {
+        std::vector<int32_t> ids, main_id, main_gene, mem_id, mem_gene;
+        std::vector<uint8_t> main_rev, mem_rev;
+        std::vector<int64_t> cl_off{0};
+        std::unique_ptr<char[]> out[3];
+        int64_t len[3] = {0, 0, 0};
+    };
+    std::vector<Part> parts(D);
+    for (int c = 0; c < nc; ++c) {
+        Part &P = parts[c % D];
+        P.ids.push_back(c);
+        P.main_id.push_back(main_id[c]);
+        P.main_rev.push_back(main_rev[c]);
+        P.main_gene.push_back(main_gene[c]);
+        for (int64_t i = cl_off[c]; i < cl_off[c + 1]; ++i) {
+            P.mem_id.push_back(mem_id[i]);
+            P.mem_rev.push_back(mem_rev[i]);
+            P.mem_gene.push_back(mem_gene[i]);
+        }
+        P.cl_off.push_back((int64_t)P.mem_id.size());
+    }
+    auto work = [&](int d) {
+        Part &P = parts[d];
+        rtl_ctx *ctx = ctxs[d];
+        size_t bases_d = 0;
+        for (int32_t id : P.mem_id) bases_d += (size_t)(f.off[id + 1] - f.off[id]);
+        check(rtl_set_labels(ctx, lab.data(), (int)lab.size()), "rtl_set_labels", ctx);
+        check(rtl_set_cluster_ids(ctx, D > 1 ? P.ids.data() : nullptr, D > 1 ? (int)P.ids.size() : 0), "rtl_set_cluster_ids", ctx);
+        // generous first guess (corrected reads are about as long as the raw ones), exact sizes on RTL_ERR_CAPACITY
+        const int64_t guess = 3 * (int64_t)bases_d + (int64_t)f.headers.size() / D + 96 * (int64_t)(P.mem_id.size() + P.ids.size()) + 4096;
+        for (int i = 0; i < 3; ++i) P.len[i] = guess;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            for (int i = 0; i < 3; ++i) P.out[i].reset(new char[(size_t)P.len[i] + 1]);  // uninitialised: untouched pages cost nothing
+            const int rc = rtl_correct_reads(ctx, f.bases.data(), f.quals.data(), f.off.data(), (uint32_t)reads.size(),
+                                             f.headers.data(), f.hoff.data(), P.main_id.data(), P.main_rev.data(),
+                                             P.main_gene.data(), P.cl_off.data(), P.mem_id.data(), P.mem_rev.data(),
+                                             P.mem_gene.data(), (int)P.ids.size(), min_occ, gap_occ, err_ratio, split, min_reads,
+                                             P.out[0].get(), &P.len[0], P.out[1].get(), &P.len[1], P.out[2].get(), &P.len[2]);
+            if (rc == RTL_OK) break;
+            if (rc != RTL_ERR_CAPACITY || attempt == 1) check(rc, "rtl_correct_reads", ctx);
+        }
+        if (trace()) fprintf(stderr, "rattle_b200: device slot %d corrected %zu clusters\n", d, P.ids.size());
+    };
+    {
+        std::vector<std::thread> th;
+        for (int d = 1; d < D; ++d) th.emplace_back(work, d);
+        work(0);
+        for (auto &t : th) t.join();
+    }
+    correction_results_t res;
+    for (int d = 0; d < D; ++d) {
+        read_set_t c = parse_fastq(std::string(parts[d].out[0].get(), (size_t)parts[d].len[0]));
+        res.corrected.insert(res.corrected.end(), std::make_move_iterator(c.begin()), std::make_move_iterator(c.end()));
+        read_set_t u = parse_fastq(std::string(parts[d].out[1].get(), (size_t)parts[d].len[1]));
+        res.uncorrected.insert(res.uncorrected.end(), std::make_move_iterator(u.begin()), std::make_move_iterator(u.end()));
+    }
+    {
+        // consensi in cluster order (correct.cpp:488-556 walks the clusters in order): every part's records are ascending
+        // in the cluster id their header starts with ("@gene_cluster_<cid> ..." / "@transcript_cluster_<cid> ...")
+        std::vector<read_set_t> cons(D);
+        std::vector<size_t> at(D, 0);
+        auto cid_of = [](const read_t &r) { return atol(r.header.c_str() + r.header.find("_cluster_") + 9); };
+        for (int d = 0; d < D; ++d) cons[d] = parse_fastq(std::string(parts[d].out[2].get(), (size_t)parts[d].len[2]));
+        while (true) {
+            int best = -1;
+            long best_cid = 0;
+            for (int d = 0; d < D; ++d)
+                if (at[d] < cons[d].size()) {
+                    const long c = cid_of(cons[d][at[d]]);
+                    if (best < 0 || c < best_cid) {
+                        best = d;
+                        best_cid = c;
+                    }
+                }
+            if (best < 0) break;
+            res.consensi.push_back(std::move(cons[best][at[best]++]));
+        }
     }
     // the reference edits the caller's reads in place (correct.cpp:338-350): reverse members are reverse-complemented,
     // every member's header gets the cluster suffix; polish reads those headers afterwards (main.cpp:685)
@@ -197,7 +431,5 @@ correction_results_t correct_reads(const cluster_set_t &clusters, read_set_t &re
                 else r.header = r.header + ",gene_cluster_" + std::to_string(gid) + ",transcript_cluster_" + std::to_string(cid);
             }
     }
-    return correction_results_t{parse_fastq(std::string(out[0].get(), (size_t)len[0])),
-                                parse_fastq(std::string(out[1].get(), (size_t)len[1])),
-                                parse_fastq(std::string(out[2].get(), (size_t)len[2]))};
+    return res;
 }

@@ -283,6 +283,8 @@ static PoaState &pstate(rtl_ctx *ctx) {
         CK(cudaFuncSetAttribute(k_poa_chain<5, -4, -8, -6, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CK(cudaFuncSetAttribute(k_poa_chain<5, -4, -8, -6, 224, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CK(cudaFuncSetAttribute(k_poa_chain<5, -4, -8, -6, 192, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(k_poa_chain<5, -4, -8, -6, 192, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(k_poa_chain<5, -4, -8, -6, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         P.n_threads = host_threads();
         if (const char *tf = getenv("RTL_TRACE_FILE")) P.trace = fopen(tf, "w");
         CK(cudaEventCreate(&P.ev_ref));
@@ -938,14 +940,18 @@ static void dev_chain_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::ve
         // for that), with a ring of 5 rows where that is what fits 54 KB.  Dynamic shared memory = the DP's profiles and
         // row ring, or — between two DPs — the working set of the graph's sort.
         const bool four = nw <= 7 && getenv("RATTLE_B200_CTAS3") == nullptr;
-        const size_t budget = four ? (size_t)54 * 1024 : (size_t)72 * 1024;
+        // experiments: one more CTA per SM (64 registers per thread, a shallower ring) for CTAs of up to 6 / of 8 warps
+        const bool five = nw <= 6 && getenv("RATTLE_B200_CTAS5") != nullptr;
+        const bool four8 = nw == 8 && getenv("RATTLE_B200_CTAS4W8") != nullptr;
+        const size_t budget = five ? (size_t)43 * 1024 : (four8 ? (size_t)54 * 1024 : (four ? (size_t)54 * 1024 : (size_t)72 * 1024));
         int K = strip_ring_rows(nw);
         while (K > 3 && ps_smem_bytes(nw, K) > budget) --K;
         const size_t smem = std::max(ps_smem_bytes(nw, K), budget);
         const int smem_cap_n = dc_sort_cap(smem);
-        auto kern = nw == 8 ? k_poa_chain<5, -4, -8, -6, 256, 3>
+        auto kern = nw == 8 ? (four8 ? k_poa_chain<5, -4, -8, -6, 256, 4> : k_poa_chain<5, -4, -8, -6, 256, 3>)
                             : (!four ? k_poa_chain<5, -4, -8, -6, 256, 3>
-                                     : (nw == 7 ? k_poa_chain<5, -4, -8, -6, 224, 4> : k_poa_chain<5, -4, -8, -6, 192, 4>));
+                                     : (nw == 7 ? k_poa_chain<5, -4, -8, -6, 224, 4>
+                                                : (five ? k_poa_chain<5, -4, -8, -6, 192, 5> : k_poa_chain<5, -4, -8, -6, 192, 4>)));
         int occ = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nw * 32, smem));
         const int grid = (int)std::min<size_t>((size_t)cnt, (size_t)ctx->n_sm * std::max(1, occ));

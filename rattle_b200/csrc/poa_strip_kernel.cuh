@@ -136,7 +136,10 @@ __device__ __forceinline__ uint4 ps_lds128(uint32_t addr) {
     return v;
 }
 
+__device__ __forceinline__ void ps_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 #else  // CUDA_EMU: "shared-space addresses" are plain pointers
+inline void ps_prefetch_l2(const void *) {}
 using ps_saddr = uintptr_t;
 #define PS_DYNAMIC_SHARED(type, name) type *name = reinterpret_cast<type *>(emu::g_smem)
 inline unsigned long long ps_lds64(ps_saddr a) { return __atomic_load_n(reinterpret_cast<unsigned long long *>(a), __ATOMIC_SEQ_CST); }
@@ -558,6 +561,15 @@ __device__ __forceinline__ int ps_traceback_warp(const PoaSJob &J, const int4 b,
             cw = cd[((size_t)tile * nst + (grp >> 5)) * 1024 + (size_t)(grp & 31) * 32 + lane];
             c_tile = tile;
             c_grp = grp;
+            // The walk goes up and to the left, about two to three graph rows per query column, and every new tile costs
+            // a DRAM latency (the codes were streamed out by the DP and are long gone from L2): 24 lanes ask L2 for the
+            // tiles the path is likely to enter next — eight tile rows upwards in this and the next two tile columns,
+            // shifted by the path's slope — so that the dependent loads of the next steps hit L2.
+            if (lane < 24) {
+                const int dc = lane >> 3, pt = tile - (lane & 7) - 2 * dc, pg = grp - dc;
+                if (pt >= 0 && pg >= 0 && (dc | (lane & 7)) != 0)
+                    ps_prefetch_l2(cd + ((size_t)pt * nst + (pg >> 5)) * 1024 + (size_t)(pg & 31) * 32);
+            }
         }
         const uint32_t wv = __shfl_sync(0xffffffffu, cw, ((row - 1) & 7) * 4 + (jj & 3));
         return (jj & 4) ? (wv >> 16) : (wv & 0xffffu);
@@ -568,6 +580,7 @@ __device__ __forceinline__ int ps_traceback_warp(const PoaSJob &J, const int4 b,
             const int rr = tile * 8 + 1 + (lane >> 2);
             rw = rr <= n ? recs32[4 * (size_t)rr + (lane & 3)] : 0u;
             r_tile = tile;
+            if (lane >= 1 && lane <= 4 && tile - lane >= 0) ps_prefetch_l2(recs32 + 4 * ((size_t)(tile - lane) * 8 + 1));
         }
         return __shfl_sync(0xffffffffu, rw, ((row - 1) & 7) * 4 + k);
     };

@@ -70,3 +70,53 @@ def test_cli_synthetic_both_strands_and_labels_match_reference_binary():
             if name == "ours":
                 assert b"labels=sa:" in open(os.path.join(d, "consensi.fq"), "rb").read()
         assert outs["ours"] == outs["ref"]
+
+
+def test_cli_iso_runs_one_batched_pass_and_matches_reference():
+    """`cluster --iso` (main.cpp:281-324 calls cluster_reads once per gene): the drop-in answers the per-gene calls from ONE
+    rtl_cluster_reads_batched pass; clusters.out equals the reference's, and equals the per-gene path's"""
+    need_dropin()
+    want = json.load(open(os.path.join(HERE, "golden", "cli_toyset.json")))["digests"]["cluster_rna_iso"]["clusters.out"]
+    with tempfile.TemporaryDirectory() as wd:
+        fq = gold.unpack_fixture(wd)
+        digests = {}
+        for name, env in (("batched", {"RATTLE_B200_TRACE": "1"}), ("per_gene", {"RATTLE_B200_NO_ISO_BATCH": "1"})):
+            d = os.path.join(wd, name)
+            os.makedirs(d)
+            p = subprocess.run([DROPIN, "cluster", "-i", fq, "-o", d, "--rna", "--iso", "-t", "4"], check=True,
+                               stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=dict(os.environ, **env))
+            if name == "batched":
+                assert b"in one batched pass" in p.stderr and b"clustering directly" not in p.stderr, p.stderr[-2000:]
+            digests[name] = gold.sha(os.path.join(d, "clusters.out"))
+        assert digests["batched"] == want and digests["per_gene"] == want
+
+
+def test_cli_several_device_slots_give_the_same_files():
+    """RATTLE_B200_DEVICES with two slots (both on GPU 0 here): genes of --iso and clusters of `correct` are split over the
+    slots and merged; clusters.out / consensi.fq byte-identical, corrected / uncorrected as multisets of records"""
+    need_dropin()
+    want = json.load(open(os.path.join(HERE, "golden", "cli_toyset.json")))["digests"]
+    env = dict(os.environ, RATTLE_B200_DEVICES="0,0", RATTLE_B200_TRACE="1")
+    with tempfile.TemporaryDirectory() as wd:
+        fq = gold.unpack_fixture(wd)
+        d = os.path.join(wd, "o")
+        os.makedirs(d)
+        p = subprocess.run([DROPIN, "cluster", "-i", fq, "-o", d, "--rna", "--iso", "-t", "4"], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env)
+        assert p.stderr.count(b"in one batched pass") == 2, p.stderr[-2000:]
+        assert gold.sha(os.path.join(d, "clusters.out")) == want["cluster_rna_iso"]["clusters.out"]
+        subprocess.run([DROPIN, "cluster", "-i", fq, "-o", d, "--rna", "-t", "4"], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, env=env)
+        p = subprocess.run([DROPIN, "correct", "-i", fq, "-c", os.path.join(d, "clusters.out"), "-o", d, "-t", "1"], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env)
+        assert p.stderr.count(b"corrected") >= 2, p.stderr[-2000:]
+        assert gold.sha(os.path.join(d, "consensi.fq")) == want["correct"]["consensi.fq"]
+        assert gold.sha(os.path.join(d, "corrected.fq"), as_multiset=True) == want["correct"]["corrected.fq"]
+        # uncorrected.fq: same records; their order depends on how the clusters were dealt to the slots
+        with tempfile.TemporaryDirectory() as wd1:
+            d1 = os.path.join(wd1, "one")
+            os.makedirs(d1)
+            subprocess.run([DROPIN, "correct", "-i", fq, "-c", os.path.join(d, "clusters.out"), "-o", d1, "-t", "1"], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            assert gold.sha(os.path.join(d1, "uncorrected.fq")) == want["correct"]["uncorrected.fq"]
+            assert gold.sha(os.path.join(d, "uncorrected.fq"), as_multiset=True) == gold.sha(os.path.join(d1, "uncorrected.fq"), as_multiset=True)
