@@ -127,6 +127,8 @@ int rtl_set_option(rtl_ctx *ctx, const char *key, int64_t value) {
         ctx->poa_gpu_sort = (int)value;
     } else if (k == "poa_device_chain") {
         ctx->poa_device_chain = (int)value;
+    } else if (k == "poa_device_vote") {
+        ctx->poa_device_vote = (int)value;
     } else if (k == "poa_kernel") {
         ctx->poa_kernel = (int)value;
     } else if (k == "poa_arena_mb") {

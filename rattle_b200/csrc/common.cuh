@@ -130,6 +130,7 @@ struct rtl_ctx {
     int poa_mirror_pct = 100;  // capacity of the device graph mirrors, percent of the default (tests)
     int poa_kernel = 0;        // 0 = int16 strip kernel where eligible, 1 = int32 kernel only
     int poa_device_chain = 1;  // 1 = whole per-pack chains on the GPU (poa_devchain.cuh), 0 = host-driven lock-steps
+    int poa_device_vote = 1;   // 1 = fix_msa_ends / column vote / read correction on the GPU (poa_vote.cuh), 0 = on the host
     int64_t poa_arena_mb = 0;  // 0 = 40 % of free device memory, at most 64 GB
     std::vector<int32_t> cluster_ids;  // global ids of the clusters of the next rtl_correct_reads calls (rtl_set_cluster_ids)
     std::vector<std::string> labels;  // file labels of `rattle correct -l` (rtl_set_labels; correct.cpp:447-470,488-512)

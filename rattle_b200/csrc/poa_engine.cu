@@ -20,6 +20,7 @@
 #include "poa_strip_kernel.cuh"
 #include "poa_devgraph.cuh"
 #include "poa_devchain.cuh"
+#include "poa_vote.cuh"
 
 using namespace rtl;
 
@@ -98,6 +99,29 @@ struct PoaSlot {
     PinBuf<uint64_t> ch_msa_off;
     DevBuf<char> c_msa;
     PinBuf<char> ch_msa;
+    // MSA post-processing on the device (poa_vote.cuh)
+    DevBuf<uint8_t> c_qual;            // the reads' qualities, laid out like c_q
+    PinBuf<uint8_t> ch_qual;
+    DevBuf<DVPack> v_packs;
+    PinBuf<DVPack> vh_packs;
+    DevBuf<DVRead> v_reads;
+    PinBuf<DVRead> vh_reads;
+    DevBuf<DVRow> v_rows;
+    PinBuf<DVRow> vh_rows;
+    DevBuf<DVCol> v_cols;
+    DevBuf<char> v_qm, v_out_seq, v_out_qual, v_cons;
+    PinBuf<char> vh_out_seq, vh_out_qual, vh_cons;
+    DevBuf<int32_t> v_len;
+    PinBuf<int32_t> vh_len;
+    DevBuf<double> v_tab;
+    DevBuf<unsigned char> v_symtab;
+    bool v_tab_ready = false;
+    DevBuf<int4> v_flagged;            // (pack, column, cerr as two words)
+    PinBuf<int4> vh_flagged;
+    DevBuf<unsigned int> v_nflag;
+    PinBuf<unsigned int> vh_nflag;
+    DevBuf<DVStage> v_stage;
+    PinBuf<DVStage> vh_stage;
 };
 
 constexpr int POA_MAX_UNITS = 16;
@@ -805,8 +829,22 @@ static ChainSizes chain_sizes(const rtl_ctx *ctx, const PoaTask *t) {
     return z;
 }
 
-static void dev_chain_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vector<PoaTask *> &batch,
-                            const std::vector<ChainSizes> &sizes, std::vector<PoaTask *> &failed) {
+// Where a chain launch takes its reads from: host strings (PoaTask::seq), optionally with their qualities (uploaded next
+// to the letter codes for the device-side vote), or corrected reads that already lie on the device (round 2 after a
+// device-side vote: `stage` lists them in table order, k_vote_stage_queries turns them into letter codes).
+struct ChainInput {
+    const std::vector<std::vector<const char *>> *quals = nullptr;  // per pack, per read
+    const std::vector<DVStage> *stage = nullptr;                     // q_off is filled in here
+    const char *stage_src = nullptr;
+};
+struct ChainRun {
+    double ts0 = 0, ts1 = 0, ts2 = 0;
+};
+
+// plan + upload + launch + wait: afterwards S.ch_packs holds every pack's status / graph size / MSA columns and the
+// graphs, paths and MSA column ids lie in the slot's device buffers
+static ChainRun chain_run(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vector<PoaTask *> &batch,
+                          const std::vector<ChainSizes> &sizes, const ChainInput &in) {
     const double ts0 = now_ms();
     cudaStream_t st = S.stream;
     const size_t np = batch.size();
@@ -830,7 +868,7 @@ static void dev_chain_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::ve
         K.path_off = (uint32_t)path_words;
         K.qnode_off = (uint32_t)qnode_words;
         K.seq_base = (uint32_t)n_seq_total;
-        K.n_seq = (int32_t)t->seq.size();
+        K.n_seq = (int32_t)t->len.size();
         K.cap_n = z.cap_n;
         K.cap_e = z.cap_e;
         K.cap_a = z.cap_a;
@@ -843,7 +881,7 @@ static void dev_chain_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::ve
         aln_pairs += (size_t)z.cap_n + z.maxlen + 8;
         path_words += (size_t)z.total;
         qnode_words += (size_t)z.maxlen + 8;
-        n_seq_total += t->seq.size();
+        n_seq_total += t->len.size();
         for (int l : t->len) q_bytes += (size_t)((l + PS_STRIP - 1) / PS_STRIP) * PS_STRIP;
     }
     if (arena_words * 4 > S.arena_bytes) throw StateError("device-chain batch exceeds the unit's arena");
@@ -860,20 +898,24 @@ static void dev_chain_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::ve
             for (int l : batch[i]->len) b += (size_t)((l + PS_STRIP - 1) / PS_STRIP) * PS_STRIP;
             qo[i + 1] = qo[i] + b;
         }
+        uint8_t *hql = in.quals ? S.ch_qual.need_geo(q_bytes + 16) : nullptr;
         parallel_for(S.n_threads, np, [&](size_t i) {
             const PoaTask *t = batch[i];
             size_t at = qo[i];
             uint32_t prel = 0;
-            for (size_t s = 0; s < t->seq.size(); ++s) {
+            for (size_t s = 0; s < t->len.size(); ++s) {
                 const int L = t->len[s], nst = (L + PS_STRIP - 1) / PS_STRIP;
                 DCSeq &Q = hs[hp[i].seq_base + s];
                 Q.q_off = (uint32_t)at;
                 Q.path_rel = prel;
                 Q.L = L;
                 Q.pad = 0;
-                const char *src = t->seq[s];
-                for (int x = 0; x < L; ++x) hq[at + x] = tab[(unsigned char)src[x]];
-                memset(hq + at + L, 255, (size_t)nst * PS_STRIP - L);
+                if (!in.stage) {
+                    const char *src = t->seq[s];
+                    for (int x = 0; x < L; ++x) hq[at + x] = tab[(unsigned char)src[x]];
+                    memset(hq + at + L, 255, (size_t)nst * PS_STRIP - L);
+                    if (hql) memcpy(hql + at, (*in.quals)[i][s], (size_t)L);
+                }
                 at += (size_t)nst * PS_STRIP;
                 prel += (uint32_t)L;
             }
@@ -920,7 +962,27 @@ static void dev_chain_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::ve
     S.c_stats.need_geo(8);
     CK(cudaMemcpyAsync(S.c_packs.need_geo(np), hp, np * sizeof(DCPack), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(S.c_seqs.need_geo(n_seq_total), hs, n_seq_total * sizeof(DCSeq), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(S.c_q.need_geo(q_bytes + 16), hq, q_bytes, cudaMemcpyHostToDevice, st));
+    S.c_q.need_geo(q_bytes + 16);
+    if (!in.stage) {
+        CK(cudaMemcpyAsync(S.c_q.p, hq, q_bytes, cudaMemcpyHostToDevice, st));
+        if (in.quals) {
+            CK(cudaMemcpyAsync(S.c_qual.need_geo(q_bytes + 16), S.ch_qual.p, q_bytes, cudaMemcpyHostToDevice, st));
+            S.st.h2d_bytes += (int64_t)q_bytes;
+        }
+    } else {  // the reads are on the device already: one CTA per read writes its letter codes
+        const size_t nr = in.stage->size();
+        if (nr != n_seq_total) throw StateError("chain_run: staging table does not match the packs");
+        DVStage *hst2 = S.vh_stage.need_geo(nr + 1);
+        for (size_t r = 0; r < nr; ++r) {
+            hst2[r] = (*in.stage)[r];
+            hst2[r].q_off = hs[r].q_off;
+        }
+        CK(cudaMemcpyAsync(S.v_stage.need_geo(nr + 1), hst2, nr * sizeof(DVStage), cudaMemcpyHostToDevice, st));
+        if (nr) k_vote_stage_queries<<<(unsigned)nr, 256, 0, st>>>(S.v_stage.p, in.stage_src, S.c_q.p, PS_STRIP);
+        CK(cudaGetLastError());
+        S.st.kernel_launches++;
+        S.st.h2d_bytes += (int64_t)(nr * sizeof(DVStage)) - (int64_t)q_bytes;
+    }
     CK(cudaMemcpyAsync(S.c_list.need_geo(np), list.data(), np * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(S.c_counter.p, 0, (n_segs + 1) * sizeof(unsigned int), st));
     CK(cudaMemsetAsync(S.c_stats.p, 0, 8 * sizeof(unsigned long long), st));
@@ -977,18 +1039,71 @@ static void dev_chain_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::ve
     slot_wait(S);
     const double ts2 = now_ms();
     S.t_wait += ts2 - ts1;
-    // ---- MSA rows of the packs that made it, compact
+    {
+        float ms = 0, k0 = 0, k1 = 0;
+        CK(cudaEventElapsedTime(&ms, S.ev0, S.ev1));
+        cudaEventElapsedTime(&k0, P.ev_ref, S.ev0);
+        cudaEventElapsedTime(&k1, P.ev_ref, S.ev1);
+        S.st.poa_ms += ms;
+        S.st.poa_cells += (int64_t)hst[0];
+        S.st.poa_alignments += (int64_t)hst[1];
+        S.st.poa_dram_bytes += (int64_t)hst[2];
+        if (getenv("RTL_TRACE")) {
+            const double tot = (double)(hst[3] + hst[4] + hst[5]);
+            fprintf(stderr, "[rtl] device chains unit %d: %zu packs, CTA clocks: graph update %.1f %% (add_alignment %.1f, sort %.1f), "
+                    "DP %.1f %%, traceback %.1f %% (%.0f ms of CTA time at 1.9 GHz)\n", (int)(&S - P.slot_store), np,
+                    100.0 * hst[3] / std::max(1.0, tot), 100.0 * hst[6] / std::max(1.0, tot), 100.0 * hst[7] / std::max(1.0, tot),
+                    100.0 * hst[4] / std::max(1.0, tot), 100.0 * hst[5] / std::max(1.0, tot), tot / 1.9e6);
+        }
+        S.st.d2h_bytes += (int64_t)(np * sizeof(DCPack) + 32);
+        std::lock_guard<std::mutex> lk(P.stats_mu);
+        P.intervals.emplace_back(k0, k1);
+        if (P.trace) {
+            fprintf(P.trace, "{\"unit\": %d, \"epoch\": %d, \"jobs\": %zu, \"stage0\": %.3f, \"stage1\": %.3f, \"k0\": %.3f, \"k1\": %.3f, "
+                    "\"sync\": %.3f, \"fold\": %.3f, \"device_chain\": 1}\n", (int)(&S - P.slot_store), S.epoch, np, ts0 - P.t_ref,
+                    ts1 - P.t_ref, k0, k1, ts2 - P.t_ref, now_ms() - P.t_ref);
+            fflush(P.trace);
+        }
+    }
+    ChainRun R;
+    R.ts0 = ts0;
+    R.ts1 = ts1;
+    R.ts2 = ts2;
+    return R;
+}
+
+// MSA rows (graph.cpp:390-426) of the packs of the last chain_run that made it, compact in S.c_msa: pack i's n_seq x ncol
+// chars start at offset hmo[i] (S.ch_msa_off); returns the total size.  Enqueued on the slot's stream.
+static size_t chain_msa_rows(PoaSlot &S, size_t np) {
+    cudaStream_t st = S.stream;
+    const DCPack *hp = S.ch_packs.p;
     uint64_t *hmo = S.ch_msa_off.need_geo(np + 1);
     size_t msa_bytes = 0;
     for (size_t i = 0; i < np; ++i) {
         hmo[i] = msa_bytes;
         if (hp[i].status == DC_OK) msa_bytes += (size_t)hp[i].n_seq * (size_t)hp[i].ncol;
     }
+    hmo[np] = msa_bytes;
     CK(cudaMemcpyAsync(S.c_msa_off.need_geo(np + 1), hmo, np * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     S.c_msa.need_geo(msa_bytes + 16);
     k_chain_msa_rows<<<(unsigned)np, 256, 0, st>>>(S.c_packs.p, S.c_seqs.p, S.c_msa_off.p, S.c_pool.p, S.c_path.p, S.c_msa.p);
     CK(cudaGetLastError());
     S.st.kernel_launches++;
+    S.st.h2d_bytes += (int64_t)(np * sizeof(uint64_t));
+    return msa_bytes;
+}
+
+// Whole chains on the GPU, MSA rows back to the host (PoaTask::msa_rows).
+static void dev_chain_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vector<PoaTask *> &batch,
+                            const std::vector<ChainSizes> &sizes, std::vector<PoaTask *> &failed) {
+    const size_t np = batch.size();
+    cudaStream_t st = S.stream;
+    const ChainRun R = chain_run(ctx, P, S, batch, sizes, ChainInput());
+    const double ts2 = R.ts2;
+    const DCPack *hp = S.ch_packs.p;
+    const size_t msa_bytes = chain_msa_rows(S, np);
+    const uint64_t *hmo = S.ch_msa_off.p;
+    // ---- MSA rows of the packs that made it, compact
     char *hm = S.ch_msa.need_geo(msa_bytes + 16);
     if (msa_bytes) CK(cudaMemcpyAsync(hm, S.c_msa.p, msa_bytes, cudaMemcpyDeviceToHost, st));
     slot_wait(S);
@@ -1005,33 +1120,7 @@ static void dev_chain_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::ve
     for (size_t i = 0; i < np; ++i)
         if (hp[i].status != DC_OK) failed.push_back(batch[i]);
     S.t_fold += now_ms() - tf0;
-    float ms = 0, k0 = 0, k1 = 0;
-    CK(cudaEventElapsedTime(&ms, S.ev0, S.ev1));
-    cudaEventElapsedTime(&k0, P.ev_ref, S.ev0);
-    cudaEventElapsedTime(&k1, P.ev_ref, S.ev1);
-    S.st.poa_ms += ms;
-    S.st.poa_cells += (int64_t)hst[0];
-    S.st.poa_alignments += (int64_t)hst[1];
-    S.st.poa_dram_bytes += (int64_t)hst[2];
-    if (getenv("RTL_TRACE")) {
-        const double tot = (double)(hst[3] + hst[4] + hst[5]);
-        fprintf(stderr, "[rtl] device chains unit %d: %zu packs, CTA clocks: graph update %.1f %% (add_alignment %.1f, sort %.1f), "
-                "DP %.1f %%, traceback %.1f %% (%.0f ms of CTA time at 1.9 GHz)\n", (int)(&S - P.slot_store), np,
-                100.0 * hst[3] / std::max(1.0, tot), 100.0 * hst[6] / std::max(1.0, tot), 100.0 * hst[7] / std::max(1.0, tot),
-                100.0 * hst[4] / std::max(1.0, tot), 100.0 * hst[5] / std::max(1.0, tot), tot / 1.9e6);
-    }
-    S.st.d2h_bytes += (int64_t)(np * sizeof(DCPack) + 32 + msa_bytes);
-    S.st.h2d_bytes += (int64_t)(np * sizeof(uint64_t));
-    {
-        std::lock_guard<std::mutex> lk(P.stats_mu);
-        P.intervals.emplace_back(k0, k1);
-        if (P.trace) {
-            fprintf(P.trace, "{\"unit\": %d, \"epoch\": %d, \"jobs\": %zu, \"stage0\": %.3f, \"stage1\": %.3f, \"k0\": %.3f, \"k1\": %.3f, "
-                    "\"sync\": %.3f, \"fold\": %.3f, \"device_chain\": 1}\n", (int)(&S - P.slot_store), S.epoch, np, ts0 - P.t_ref,
-                    ts1 - P.t_ref, k0, k1, ts2 - P.t_ref, now_ms() - P.t_ref);
-            fflush(P.trace);
-        }
-    }
+    S.st.d2h_bytes += (int64_t)msa_bytes;
 }
 
 static void poa_chain_host(rtl_ctx *ctx, PoaState &P, PoaSlot &S, int unit, std::vector<PoaTask *> &tasks, int sm, int sn,
@@ -1124,6 +1213,364 @@ void poa_chain(rtl_ctx *ctx, int unit, std::vector<PoaTask *> &tasks, int sm, in
             fprintf(stderr, "[rtl] poa_chain unit %d: %zu tasks (%zu on the device chain, %zu of them sent back, %zu host-driven), "
                     "%.1f ms (waited for GPU %.1f, host fold/MSA %.1f, stage+submit %.1f), %d host threads\n", unit, tasks.size(),
                     n_dev, n_failed, rest.size(), now_ms() - t_begin, S.t_wait, S.t_fold, S.t_stage, S.n_threads);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ device-side vote
+// correct.cpp:395-445 for one batch of packs without the MSAs leaving the GPU: chains of round 1 -> MSA rows -> fix_msa_ends
+// + per-cell qualities (k_vote_rows) -> column statistics (k_vote_cols) -> the few quality symbols that need the host's
+// log10 -> corrected reads (k_vote_apply) -> [host: lengths, order of round 2] -> chains of round 2 on the corrected reads,
+// staged device to device -> MSA rows -> fix_msa_ends + vote -> consensus.  D2H traffic: corrected reads and consensi.
+
+static void vote_tables(PoaSlot &S, double *tab, unsigned char *symtab) {
+    for (int i = 0; i < 256; ++i) {
+        const double q = (char)i - 33;  // utils.cpp:11-13 (phred_err of a char)
+        tab[i] = pow(10.0, -q / 10.0);
+        symtab[i] = (unsigned char)(char)(-10 * log10(tab[i]) + 33);  // utils.cpp:6-9 (phred_symbol)
+    }
+    (void)S;
+}
+
+struct VoteRound1 {           // what round 2 needs from round 1, per pack of the batch
+    std::vector<int> order;   // rows of the corrected reads, longest first (stable: fasta.cpp:458-464)
+    uint64_t out_off = 0;     // the pack's block in v_out_seq
+    int ncol = 0;
+    bool ok = false;
+};
+
+static void vote_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vector<VotePack *> &packs, std::vector<PoaTask> &tasks,
+                       const std::vector<ChainSizes> &sizes, double min_occ, double gap_occ) {
+    cudaStream_t st = S.stream;
+    const size_t np = packs.size();
+    if (!S.v_tab_ready) {
+        double tab[256];
+        unsigned char symtab[256];
+        vote_tables(S, tab, symtab);
+        CK(cudaMemcpyAsync(S.v_tab.need(256), tab, sizeof(tab), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(S.v_symtab.need(256), symtab, sizeof(symtab), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));  // the tables are on this stack frame
+        S.v_tab_ready = true;
+    }
+    // ---- round 1: chains
+    std::vector<PoaTask *> batch(np);
+    std::vector<std::vector<const char *>> quals(np);
+    for (size_t i = 0; i < np; ++i) {
+        batch[i] = &tasks[i];
+        quals[i] = packs[i]->qual;
+    }
+    ChainInput in1;
+    in1.quals = &quals;
+    chain_run(ctx, P, S, batch, sizes, in1);
+    const size_t msa_bytes = chain_msa_rows(S, np);
+    // ---- round 1: vote
+    const double tv0 = now_ms();
+    std::vector<VoteRound1> r1(np);
+    size_t n_rows = 0, n_cols = 0;
+    int max_ncol = 1;
+    {
+        const DCPack *hp = S.ch_packs.p;
+        const DCSeq *hs = S.ch_seqs.p;
+        const uint64_t *hmo = S.ch_msa_off.p;
+        for (size_t i = 0; i < np; ++i) n_rows = std::max<size_t>(n_rows, (size_t)hp[i].seq_base + (size_t)hp[i].n_seq);
+        DVPack *vp = S.vh_packs.need_geo(np);
+        DVRead *vr = S.vh_reads.need_geo(n_rows + 1);
+        for (size_t i = 0; i < np; ++i) {
+            DVPack &V = vp[i];
+            memset(&V, 0, sizeof(V));
+            const bool ok = hp[i].status == DC_OK;
+            V.msa_off = hmo[i];
+            V.out_off = hmo[i];
+            V.col_off = n_cols;
+            V.row_base = hp[i].seq_base;
+            V.seq_base = hp[i].seq_base;
+            V.n_seq = hp[i].n_seq;
+            V.ncol = ok ? hp[i].ncol : 0;
+            V.status = ok ? DV_OK : DV_DEGENERATE;
+            if (ok) {
+                n_cols += (size_t)hp[i].ncol;
+                max_ncol = std::max(max_ncol, hp[i].ncol);
+            }
+            for (int s2 = 0; s2 < hp[i].n_seq; ++s2) {
+                DVRead &R = vr[hp[i].seq_base + s2];
+                R.qual_off = hs[hp[i].seq_base + s2].q_off;
+                R.L = hs[hp[i].seq_base + s2].L;
+                R.pad = 0;
+            }
+            r1[i].out_off = hmo[i];
+            r1[i].ncol = V.ncol;
+        }
+        CK(cudaMemcpyAsync(S.v_packs.need_geo(np), vp, np * sizeof(DVPack), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(S.v_reads.need_geo(n_rows + 1), vr, n_rows * sizeof(DVRead), cudaMemcpyHostToDevice, st));
+        S.st.h2d_bytes += (int64_t)(np * sizeof(DVPack) + n_rows * sizeof(DVRead));
+    }
+    S.v_rows.need_geo(n_rows + 1);
+    S.v_cols.need_geo(n_cols + 1);
+    S.v_qm.need_geo(msa_bytes + 16);
+    S.v_out_seq.need_geo(msa_bytes + 16);
+    S.v_out_qual.need_geo(msa_bytes + 16);
+    S.v_len.need_geo(n_rows + 1);
+    S.v_flagged.need_geo(n_cols + 1);
+    CK(cudaMemsetAsync(S.v_nflag.need(1), 0, sizeof(unsigned int), st));
+    const unsigned int flag_cap = (unsigned int)std::min<size_t>(n_cols, 0x7fffffffu);
+    k_vote_rows<<<(unsigned)np, 64, 0, st>>>(S.v_packs.p, S.v_reads.p, S.c_msa.p, S.v_qm.p, reinterpret_cast<const char *>(S.c_qual.p),
+                                             S.v_rows.p, 1);
+    CK(cudaGetLastError());
+    k_vote_cols<<<dim3((unsigned)((max_ncol + 127) / 128), (unsigned)np), 128, 0, st>>>(
+        S.v_packs.p, S.c_msa.p, S.v_qm.p, S.v_rows.p, S.v_tab.p, S.v_symtab.p, S.v_cols.p, 1, S.v_flagged.p, S.v_nflag.p, flag_cap);
+    CK(cudaGetLastError());
+    S.st.kernel_launches += 2;
+    unsigned int *hnf = S.vh_nflag.need(1);
+    CK(cudaMemcpyAsync(hnf, S.v_nflag.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    slot_wait(S);
+    if (*hnf > flag_cap) throw StateError("vote: more flagged columns than columns");
+    if (*hnf) {  // the host's libm decides these quality symbols (poa_vote.cuh)
+        const unsigned int nf = *hnf;
+        int4 *hf = S.vh_flagged.need_geo(nf);
+        CK(cudaMemcpyAsync(hf, S.v_flagged.p, (size_t)nf * sizeof(int4), cudaMemcpyDeviceToHost, st));
+        slot_wait(S);
+        for (unsigned int x = 0; x < nf; ++x) {
+            const unsigned long long bits = (unsigned long long)(unsigned int)hf[x].z | ((unsigned long long)(unsigned int)hf[x].w << 32);
+            double cerr;
+            memcpy(&cerr, &bits, 8);
+            hf[x].z = (int)(char)(-10 * log10(cerr) + 33);  // utils.cpp:6-9
+            hf[x].w = 0;
+        }
+        CK(cudaMemcpyAsync(S.v_flagged.p, hf, (size_t)nf * sizeof(int4), cudaMemcpyHostToDevice, st));
+        k_vote_patch<<<(nf + 255) / 256, 256, 0, st>>>(S.v_flagged.p, nf, S.v_cols.p);
+        CK(cudaGetLastError());
+        S.st.kernel_launches++;
+        S.st.d2h_bytes += (int64_t)nf * 16;
+        S.st.h2d_bytes += (int64_t)nf * 16;
+    }
+    k_vote_apply<<<(unsigned)np, 64, 0, st>>>(S.v_packs.p, S.c_msa.p, S.v_qm.p, S.v_rows.p, S.v_cols.p, S.v_tab.p, min_occ, gap_occ,
+                                              S.v_out_seq.p, S.v_out_qual.p, S.v_len.p);
+    CK(cudaGetLastError());
+    S.st.kernel_launches++;
+    DVPack *vp = S.vh_packs.p;
+    DVRow *hrows = S.vh_rows.need_geo(n_rows + 1);
+    int32_t *hlen = S.vh_len.need_geo(n_rows + 1);
+    char *hos = S.vh_out_seq.need_geo(msa_bytes + 16);
+    char *hoq = S.vh_out_qual.need_geo(msa_bytes + 16);
+    CK(cudaMemcpyAsync(vp, S.v_packs.p, np * sizeof(DVPack), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hrows, S.v_rows.p, n_rows * sizeof(DVRow), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hlen, S.v_len.p, n_rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (msa_bytes) {
+        CK(cudaMemcpyAsync(hos, S.v_out_seq.p, msa_bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hoq, S.v_out_qual.p, msa_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    slot_wait(S);
+    S.st.d2h_bytes += (int64_t)(np * sizeof(DVPack) + n_rows * (sizeof(DVRow) + 4) + 2 * msa_bytes);
+    const double tv1 = now_ms();
+    // ---- host: corrected reads of every pack, order of round 2
+    parallel_for(S.n_threads, np, [&](size_t i) {
+        VotePack &K = *packs[i];
+        const DVPack &V = vp[i];
+        r1[i].ok = V.status == DV_OK;
+        if (!r1[i].ok) return;
+        const int n = V.n_seq;
+        K.tf.resize(n);
+        K.tb.resize(n);
+        K.cseq.assign(n, std::string());
+        K.cqual.assign(n, std::string());
+        for (int r = 0; r < n; ++r) {
+            K.tf[r] = hrows[V.row_base + r].tf;
+            K.tb[r] = hrows[V.row_base + r].tb;
+            const int len = hlen[V.row_base + r];
+            if (len > 0) {
+                K.cseq[r].assign(hos + V.out_off + (size_t)r * V.ncol, (size_t)len);
+                K.cqual[r].assign(hoq + V.out_off + (size_t)r * V.ncol, (size_t)len);
+                r1[i].order.push_back(r);
+            }
+        }
+        std::stable_sort(r1[i].order.begin(), r1[i].order.end(),
+                         [&](int a, int b) { return K.cseq[a].size() > K.cseq[b].size(); });
+    });
+    const double tv2 = now_ms();
+    // ---- round 2: chains on the corrected reads (device to device), in sub-batches that fit the arena
+    std::vector<size_t> todo;
+    for (size_t i = 0; i < np; ++i) {
+        if (!r1[i].ok) continue;
+        if (r1[i].order.empty()) {  // nothing was corrected: empty consensus (correct.cpp:427-445 on an empty read set)
+            packs[i]->consensus.clear();
+            packs[i]->done = true;
+            continue;
+        }
+        todo.push_back(i);
+    }
+    std::vector<PoaTask> t2(todo.size());
+    std::vector<ChainSizes> z2(todo.size());
+    const int maxabs = 8;
+    for (size_t x = 0; x < todo.size(); ++x) {
+        const size_t i = todo[x];
+        for (int r : r1[i].order) t2[x].len.push_back((int)packs[i]->cseq[r].size());
+        z2[x] = chain_sizes(ctx, &t2[x]);
+        for (int l : t2[x].len)
+            if ((int64_t)maxabs * (l + 16) >= 32000) z2[x].arena_bytes = ~(size_t)0;  // leaves int16: host path
+    }
+    size_t x0 = 0;
+    while (x0 < todo.size()) {
+        std::vector<PoaTask *> b2;
+        std::vector<ChainSizes> s2;
+        std::vector<DVStage> stage;
+        std::vector<size_t> who;
+        size_t used = 0, x1 = x0;
+        for (; x1 < todo.size(); ++x1) {
+            if (z2[x1].arena_bytes > S.arena_bytes) {  // cannot run here: the caller redoes the pack on the host path
+                if (b2.empty()) {
+                    ++x1;
+                    break;
+                }
+                break;
+            }
+            if (used + z2[x1].arena_bytes > S.arena_bytes) break;
+            used += z2[x1].arena_bytes;
+            const size_t i = todo[x1];
+            b2.push_back(&t2[x1]);
+            s2.push_back(z2[x1]);
+            who.push_back(i);
+            for (int r : r1[i].order) {
+                DVStage e;
+                e.src_off = r1[i].out_off + (uint64_t)r * (uint64_t)r1[i].ncol;
+                e.q_off = 0;
+                e.L = (int32_t)packs[i]->cseq[r].size();
+                stage.push_back(e);
+            }
+        }
+        x0 = x1;
+        if (b2.empty()) continue;
+        ChainInput in2;
+        in2.stage = &stage;
+        in2.stage_src = S.v_out_seq.p;
+        chain_run(ctx, P, S, b2, s2, in2);
+        const size_t nb = b2.size();
+        const size_t msa2 = chain_msa_rows(S, nb);
+        const DCPack *hp = S.ch_packs.p;
+        const uint64_t *hmo = S.ch_msa_off.p;
+        DVPack *v2 = S.vh_packs.need_geo(nb);
+        size_t rows2 = 0, cols2 = 0;
+        int max2 = 1;
+        for (size_t k = 0; k < nb; ++k) {
+            DVPack &V = v2[k];
+            memset(&V, 0, sizeof(V));
+            const bool ok = hp[k].status == DC_OK;
+            V.msa_off = hmo[k];
+            V.out_off = cols2;  // the consensus goes to v_cons + out_off
+            V.col_off = cols2;
+            V.row_base = hp[k].seq_base;
+            V.seq_base = hp[k].seq_base;
+            V.n_seq = hp[k].n_seq;
+            V.ncol = ok ? hp[k].ncol : 0;
+            V.status = ok ? DV_OK : DV_DEGENERATE;
+            if (ok) {
+                cols2 += (size_t)hp[k].ncol;
+                max2 = std::max(max2, hp[k].ncol);
+            }
+            rows2 = std::max<size_t>(rows2, (size_t)hp[k].seq_base + (size_t)hp[k].n_seq);
+        }
+        CK(cudaMemcpyAsync(S.v_packs.need_geo(nb), v2, nb * sizeof(DVPack), cudaMemcpyHostToDevice, st));
+        S.v_rows.need_geo(rows2 + 1);
+        S.v_cols.need_geo(cols2 + 1);
+        S.v_cons.need_geo(cols2 + 16);
+        S.v_flagged.need_geo(1);
+        CK(cudaMemsetAsync(S.v_nflag.need(1), 0, sizeof(unsigned int), st));
+        k_vote_rows<<<(unsigned)nb, 64, 0, st>>>(S.v_packs.p, S.v_reads.p, S.c_msa.p, S.v_qm.p, nullptr, S.v_rows.p, 0);
+        CK(cudaGetLastError());
+        k_vote_cols<<<dim3((unsigned)((max2 + 127) / 128), (unsigned)nb), 128, 0, st>>>(
+            S.v_packs.p, S.c_msa.p, S.v_qm.p, S.v_rows.p, S.v_tab.p, S.v_symtab.p, S.v_cols.p, 0, S.v_flagged.p, S.v_nflag.p, 0u);
+        CK(cudaGetLastError());
+        k_vote_consensus<<<(unsigned)nb, 32, 0, st>>>(S.v_packs.p, S.v_cols.p, S.v_cons.p);
+        CK(cudaGetLastError());
+        S.st.kernel_launches += 3;
+        char *hc = S.vh_cons.need_geo(cols2 + 16);
+        CK(cudaMemcpyAsync(v2, S.v_packs.p, nb * sizeof(DVPack), cudaMemcpyDeviceToHost, st));
+        if (cols2) CK(cudaMemcpyAsync(hc, S.v_cons.p, cols2, cudaMemcpyDeviceToHost, st));
+        slot_wait(S);
+        S.st.h2d_bytes += (int64_t)(nb * sizeof(DVPack));
+        S.st.d2h_bytes += (int64_t)(nb * sizeof(DVPack) + cols2);
+        (void)msa2;
+        for (size_t k = 0; k < nb; ++k) {
+            if (v2[k].status != DV_OK) continue;  // stays !done: host path
+            VotePack &K = *packs[who[k]];
+            K.consensus.assign(hc + v2[k].out_off, (size_t)v2[k].cons_len);
+            K.done = true;
+        }
+    }
+    if (getenv("RTL_TRACE"))
+        fprintf(stderr, "[rtl] device vote unit %d: %zu packs, round-1 vote kernels + D2H %.1f ms, host strings %.1f ms, round 2 %.1f ms\n",
+                (int)(&S - P.slot_store), np, tv1 - tv0, tv2 - tv1, now_ms() - tv2);
+}
+
+void poa_correct_unit(rtl_ctx *ctx, int unit, std::vector<VotePack *> &packs, double min_occ, double gap_occ, int n_threads) {
+    PoaState &P = pstate(ctx);
+    if (unit < 0 || unit >= P.n_units) throw StateError("poa_correct_unit: no such unit");
+    CK(cudaSetDevice(ctx->device));
+    PoaSlot &S = P.slot_store[unit];
+    S.n_threads = std::max(1, n_threads);
+    S.t_wait = S.t_fold = S.t_stage = 0;
+    S.st = rtl_stats{};
+    S.epoch++;
+    const double t_begin = now_ms();
+    const uint8_t *tab = letter_codes();
+    std::vector<PoaTask> tasks(packs.size());
+    std::vector<uint8_t> elig(packs.size(), 0);
+    const bool dev_ok = ctx->poa_device_chain != 0 && ctx->poa_gpu_sort != 0 && ctx->poa_kernel != 1;
+    parallel_for(S.n_threads, packs.size(), [&](size_t i) {
+        VotePack &K = *packs[i];
+        K.done = false;
+        PoaTask &t = tasks[i];
+        t.seq = K.seq;
+        t.len = K.len;
+        bool ok = dev_ok && !K.seq.empty() && K.seq.size() == K.qual.size();
+        for (size_t s2 = 0; s2 < K.seq.size() && ok; ++s2) {
+            const int l = K.len[s2];
+            if (l < 1 || (int64_t)8 * (l + 16) >= 32000) ok = false;
+            for (int x = 0; x < l && ok; ++x)
+                if (tab[(unsigned char)K.seq[s2][x]] == 255) ok = false;
+        }
+        elig[i] = ok;
+    });
+    std::vector<VotePack *> bp;
+    std::vector<PoaTask> bt;
+    std::vector<ChainSizes> bz;
+    size_t used = 0;
+    size_t n_dev = 0;
+    auto flush = [&]() {
+        if (bp.empty()) return;
+        n_dev += bp.size();
+        vote_batch(ctx, P, S, bp, bt, bz, min_occ, gap_occ);
+        bp.clear();
+        bt.clear();
+        bz.clear();
+        used = 0;
+    };
+    for (size_t i = 0; i < packs.size(); ++i) {
+        if (!elig[i]) continue;
+        const ChainSizes z = chain_sizes(ctx, &tasks[i]);
+        if (z.arena_bytes > S.arena_bytes) continue;
+        if (used + z.arena_bytes > S.arena_bytes) flush();
+        bp.push_back(packs[i]);
+        bt.push_back(tasks[i]);
+        bz.push_back(z);
+        used += z.arena_bytes;
+    }
+    flush();
+    {
+        std::lock_guard<std::mutex> lk(P.stats_mu);
+        rtl_stats &d = ctx->stats;
+        d.h2d_bytes += S.st.h2d_bytes;
+        d.d2h_bytes += S.st.d2h_bytes;
+        d.poa_launches += S.st.poa_launches;
+        d.kernel_launches += S.st.kernel_launches;
+        d.poa_alignments += S.st.poa_alignments;
+        d.poa_cells += S.st.poa_cells;
+        d.poa_dram_bytes += S.st.poa_dram_bytes;
+        d.poa_ms += S.st.poa_ms;
+        size_t n_done = 0;
+        for (auto *k : packs) n_done += k->done;
+        if (getenv("RTL_TRACE"))
+            fprintf(stderr, "[rtl] poa_correct_unit %d: %zu packs (%zu on the device pipeline, %zu finished there), %.1f ms "
+                    "(waited for GPU %.1f, stage+submit %.1f), %d host threads\n", unit, packs.size(), n_dev, n_done,
+                    now_ms() - t_begin, S.t_wait, S.t_stage, S.n_threads);
     }
 }
 

@@ -48,4 +48,18 @@ void run_units(int n_units, const std::function<void(int)> &fn);
 void poa_chain(rtl_ctx *ctx, int unit, std::vector<PoaTask *> &tasks, int m, int n, int g, int e, bool keep_alns,
                int n_threads);
 void parallel_for(int n_threads, size_t n, const std::function<void(size_t)> &fn);
+
+// One pack of correct_reads whose whole pipeline (correct.cpp:395-445: POA round 1, fix_msa_ends, column vote, read
+// correction, POA round 2 on the corrected reads, fix_msa_ends, vote -> consensus) runs on the GPU (poa_vote.cuh): the MSAs
+// never travel to the host.
+struct VotePack {
+    std::vector<const char *> seq, qual;  // the pack's reads in POA order (views; the caller keeps them alive)
+    std::vector<int> len;
+    bool done = false;                    // false after the call: the caller runs the host pipeline for this pack
+    std::vector<int32_t> tf, tb;          // bases fix_msa_ends (round 1) removed at the front / the back of every read
+    std::vector<std::string> cseq, cqual; // corrected read per input read; empty = the read stays uncorrected
+    std::string consensus;
+};
+// one unit's packs through that pipeline, synchronously, on the unit's stream / arena slice (like poa_chain)
+void poa_correct_unit(rtl_ctx *ctx, int unit, std::vector<VotePack *> &packs, double min_occ, double gap_occ, int n_threads);
 int host_threads();
