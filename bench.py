@@ -436,25 +436,29 @@ def main():
                      "poa_cells": st2["poa_cells"] if st2 else 0, "poa_alignments": st2["poa_alignments"] if st2 else 0,
                      **digests},
     }
-    # ---- the bitvector scan in its streaming regime (1 and 2 seeds against every read of the workload, the regime
-    # BASELINE.json's >= 50 %-of-HBM target is about), through the C ABI (rtl_bv_scan), L2 flushed before every launch
+    # ---- the bitvector scan in its streaming regime (1, 2 and 4 seeds against every read — the regime BASELINE.json's
+    # >= 50 %-of-HBM target is about), through the C ABI (rtl_bv_scan).  The read set is the same generator at 400 k reads
+    # (410 MB of bitvectors, 3x the L2) and the L2 is flushed before every launch, so every byte comes from HBM.
     if world == 1:
         try:
+            big = make_workload(8000)
+            ctx.upload(big.bases, big.offsets)
             flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-            targets = np.arange(n_reads, dtype=np.int32)
+            targets = np.arange(big.n, dtype=np.int32)
             stream_lines = []
-            for ns in (1, 2):
-                seeds = np.linspace(0, n_reads - 1, ns).astype(np.int32)
+            for ns in (1, 2, 4):
+                seeds = np.linspace(0, big.n - 1, ns).astype(np.int32)
                 times = []
-                for _ in range(5):
+                for _ in range(7):
                     flush.zero_()
                     torch.cuda.synchronize()
                     ctx.bv_scan(seeds, targets, 0.4, kmer_size=10, is_rna=False, want_output=False)
                     times.append(ctx.stats()["bv_ms"])
-                ms = float(np.median(times))
-                gbs = n_reads * (512 * S + 4) / (ms * 1e-3) / 1e9  # every read's bitvectors streamed once
+                ms = float(np.median(times[2:]))  # (the first launches also extract the k-mers of the new read set)
+                gbs = big.n * (512 * S + 4) / (ms * 1e-3) / 1e9  # every read's bitvectors streamed once
                 stream_lines.append({"seeds": ns, "kernel_ms": ms, "streamed_GBps": gbs, "frac_of_hbm": gbs / hbm})
-            line["bv_scan"]["streaming"] = {"reads": n_reads, "bytes_per_read": 512 * S + 4, "l2": "flushed (512 MB memset) before every launch",
+            line["bv_scan"]["streaming"] = {"reads": int(big.n), "bytes_per_read": 512 * S + 4,
+                                           "l2": "flushed (512 MB memset) before every launch; 410 MB streamed per launch",
                                            "runs": stream_lines}
             del flush
         except Exception as e:

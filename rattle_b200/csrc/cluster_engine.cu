@@ -103,7 +103,8 @@ static void set_smem_attrs(ClusterState &S) {
     const int max_smem = 227 * 1024;
     CK(cudaFuncSetAttribute(k_extract_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     // (k_bv_scan also holds a statically allocated mbarrier: its dynamic limit is what a full seed tile needs)
-    CK(cudaFuncSetAttribute(k_bv_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, BVS_TS * (64 * 8 + 8)));
+    CK(cudaFuncSetAttribute(k_bv_scan<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BVS_TS * (64 * 8 + 8)));
+    CK(cudaFuncSetAttribute(k_bv_scan<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, BVS_TS * (64 * 8 + 8)));
     CK(cudaFuncSetAttribute(k_bv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CK(cudaFuncSetAttribute(k_join_count, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CK(cudaFuncSetAttribute(k_pair_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -281,7 +282,8 @@ static void launch_bv_scan(rtl_ctx *ctx, BvScanArgs a, int64_t n_targets, int ma
         a.ts_cap = std::max(1, std::min(BVS_TS, max_seeds));
         int gx = (int)std::min<int64_t>((n_targets + 15) / 16, (int64_t)ctx->n_sm * 8);
         dim3 grid(std::max(gx, 1), (max_seeds + a.ts_cap - 1) / a.ts_cap);
-        k_bv_scan<<<grid, BVS_THREADS, (size_t)a.ts_cap * (64 * 8 + 8), st>>>(a);
+        if (ctx->bv_kernel == 3) k_bv_scan<3><<<grid, BVS_THREADS, (size_t)a.ts_cap * (64 * 8 + 8), st>>>(a);
+        else k_bv_scan<4><<<grid, BVS_THREADS, (size_t)a.ts_cap * (64 * 8 + 8), st>>>(a);
     } else {
         a.ts_cap = std::max(1, max_seeds);
         const size_t smem = bvt_smem_bytes(a.ts_cap);

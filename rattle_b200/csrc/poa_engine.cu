@@ -66,6 +66,8 @@ struct PoaSlot {
     PinBuf<PoaSJob> h_sjobs;
     PinBuf<uint4> h_rec;
     cudaStream_t stream = nullptr;
+    cudaStream_t hi = nullptr;  // high priority: the small kernels between two chain launches (MSA rows, vote) must not queue
+                                // behind the other units' long-running chain CTAs
     static constexpr int N_SUB = 4, N_SEG_EV = 16;
     cudaStream_t sub[N_SUB] = {nullptr, nullptr, nullptr, nullptr};  // segments of one group run side by side
     cudaEvent_t ev_seg[N_SEG_EV] = {};
@@ -145,6 +147,7 @@ void poa_state_free(rtl_ctx *ctx) {
             if (sl.ev0) cudaEventDestroy(sl.ev0);
             if (sl.ev1) cudaEventDestroy(sl.ev1);
             if (sl.stream) cudaStreamDestroy(sl.stream);
+            if (sl.hi) cudaStreamDestroy(sl.hi);
             for (auto &x : sl.sub)
                 if (x) cudaStreamDestroy(x);
             for (auto &x : sl.ev_seg)
@@ -270,13 +273,17 @@ int host_threads() {
 }
 
 // wait for everything enqueued on the slot's stream without spinning
-static void slot_wait(PoaSlot &S) {
-    CK(cudaEventRecord(S.ev_wait, S.stream));
+static void slot_wait(PoaSlot &S, cudaStream_t st = nullptr) {
+    CK(cudaEventRecord(S.ev_wait, st ? st : S.stream));
     CK(cudaEventSynchronize(S.ev_wait));
 }
 
 static PoaState &pstate(rtl_ctx *ctx) {
     if (!ctx->poa) {
+        // one context at a time: contexts of one process may share a device (the drop-in's device slots), and each sizes
+        // its arena from the memory that is free at that moment
+        static std::mutex create_mu;
+        std::lock_guard<std::mutex> create_lock(create_mu);
         ctx->poa = new PoaState();
         PoaState &P = *ctx->poa;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&P.occ[0], k_poa_align<false>, POA_T, 0));
@@ -286,12 +293,26 @@ static PoaState &pstate(rtl_ctx *ctx) {
         size_t budget = ctx->poa_arena_mb > 0 ? ((size_t)ctx->poa_arena_mb << 20) : std::min<size_t>(free_b / 2, 96ull << 30);
         budget = std::max<size_t>(budget, 64ull << 20);
         const int n_units = std::max(1, std::min(ctx->poa_units > 0 ? ctx->poa_units : 12, POA_MAX_UNITS));
-        const size_t part = (budget / n_units) & ~(size_t)255;
-        P.arena.need(n_units * part);
+        size_t part = (budget / n_units) & ~(size_t)255;
+        while (true) {  // (another process may have taken memory since cudaMemGetInfo: settle for less)
+            try {
+                P.arena.need(n_units * part);
+                break;
+            } catch (const CudaError &) {
+                cudaGetLastError();
+                if (ctx->poa_arena_mb > 0 || part * n_units <= (256ull << 20)) throw;
+                part = (part / 2) & ~(size_t)255;
+            }
+        }
         P.n_units = n_units;
         for (int i = 0; i < n_units; ++i) {
             PoaSlot &sl = P.slot_store[i];
             CK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+            {
+                int lo = 0, hi = 0;
+                CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                CK(cudaStreamCreateWithPriority(&sl.hi, cudaStreamNonBlocking, hi));
+            }
             CK(cudaEventCreate(&sl.ev0));
             CK(cudaEventCreate(&sl.ev1));
             CK(cudaEventCreate(&sl.ev_h2d));
@@ -1004,7 +1025,8 @@ static ChainRun chain_run(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vect
         const bool four = nw <= 7 && getenv("RATTLE_B200_CTAS3") == nullptr;
         // experiments: one more CTA per SM (64 registers per thread, a shallower ring) for CTAs of up to 6 / of 8 warps
         const bool five = nw <= 6 && getenv("RATTLE_B200_CTAS5") != nullptr;
-        const bool four8 = nw == 8 && getenv("RATTLE_B200_CTAS4W8") != nullptr;
+        // 8-warp CTAs: four per SM at 64 registers (8 bytes of spill) beat three at 80: +8 % on 2 kb reads (config 4)
+        const bool four8 = nw == 8 && getenv("RATTLE_B200_CTAS3") == nullptr;
         const size_t budget = five ? (size_t)43 * 1024 : (four8 ? (size_t)54 * 1024 : (four ? (size_t)54 * 1024 : (size_t)72 * 1024));
         int K = strip_ring_rows(nw);
         while (K > 3 && ps_smem_bytes(nw, K) > budget) --K;
@@ -1074,8 +1096,7 @@ static ChainRun chain_run(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vect
 
 // MSA rows (graph.cpp:390-426) of the packs of the last chain_run that made it, compact in S.c_msa: pack i's n_seq x ncol
 // chars start at offset hmo[i] (S.ch_msa_off); returns the total size.  Enqueued on the slot's stream.
-static size_t chain_msa_rows(PoaSlot &S, size_t np) {
-    cudaStream_t st = S.stream;
+static size_t chain_msa_rows(PoaSlot &S, size_t np, cudaStream_t st) {
     const DCPack *hp = S.ch_packs.p;
     uint64_t *hmo = S.ch_msa_off.need_geo(np + 1);
     size_t msa_bytes = 0;
@@ -1101,7 +1122,7 @@ static void dev_chain_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::ve
     const ChainRun R = chain_run(ctx, P, S, batch, sizes, ChainInput());
     const double ts2 = R.ts2;
     const DCPack *hp = S.ch_packs.p;
-    const size_t msa_bytes = chain_msa_rows(S, np);
+    const size_t msa_bytes = chain_msa_rows(S, np, st);
     const uint64_t *hmo = S.ch_msa_off.p;
     // ---- MSA rows of the packs that made it, compact
     char *hm = S.ch_msa.need_geo(msa_bytes + 16);
@@ -1240,7 +1261,9 @@ struct VoteRound1 {           // what round 2 needs from round 1, per pack of th
 
 static void vote_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vector<VotePack *> &packs, std::vector<PoaTask> &tasks,
                        const std::vector<ChainSizes> &sizes, double min_occ, double gap_occ) {
-    cudaStream_t st = S.stream;
+    // chain_run waits for its chains, and everything below waits for its own work before the next chain_run: the
+    // high-priority stream needs no events against the unit's stream
+    cudaStream_t st = S.hi;
     const size_t np = packs.size();
     if (!S.v_tab_ready) {
         double tab[256];
@@ -1261,7 +1284,7 @@ static void vote_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vector<
     ChainInput in1;
     in1.quals = &quals;
     chain_run(ctx, P, S, batch, sizes, in1);
-    const size_t msa_bytes = chain_msa_rows(S, np);
+    const size_t msa_bytes = chain_msa_rows(S, np, st);
     // ---- round 1: vote
     const double tv0 = now_ms();
     std::vector<VoteRound1> r1(np);
@@ -1321,13 +1344,13 @@ static void vote_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vector<
     S.st.kernel_launches += 2;
     unsigned int *hnf = S.vh_nflag.need(1);
     CK(cudaMemcpyAsync(hnf, S.v_nflag.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-    slot_wait(S);
+    slot_wait(S, st);
     if (*hnf > flag_cap) throw StateError("vote: more flagged columns than columns");
     if (*hnf) {  // the host's libm decides these quality symbols (poa_vote.cuh)
         const unsigned int nf = *hnf;
         int4 *hf = S.vh_flagged.need_geo(nf);
         CK(cudaMemcpyAsync(hf, S.v_flagged.p, (size_t)nf * sizeof(int4), cudaMemcpyDeviceToHost, st));
-        slot_wait(S);
+        slot_wait(S, st);
         for (unsigned int x = 0; x < nf; ++x) {
             const unsigned long long bits = (unsigned long long)(unsigned int)hf[x].z | ((unsigned long long)(unsigned int)hf[x].w << 32);
             double cerr;
@@ -1358,7 +1381,7 @@ static void vote_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vector<
         CK(cudaMemcpyAsync(hos, S.v_out_seq.p, msa_bytes, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(hoq, S.v_out_qual.p, msa_bytes, cudaMemcpyDeviceToHost, st));
     }
-    slot_wait(S);
+    slot_wait(S, st);
     S.st.d2h_bytes += (int64_t)(np * sizeof(DVPack) + n_rows * (sizeof(DVRow) + 4) + 2 * msa_bytes);
     const double tv1 = now_ms();
     // ---- host: corrected reads of every pack, order of round 2
@@ -1443,7 +1466,7 @@ static void vote_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vector<
         in2.stage_src = S.v_out_seq.p;
         chain_run(ctx, P, S, b2, s2, in2);
         const size_t nb = b2.size();
-        const size_t msa2 = chain_msa_rows(S, nb);
+        const size_t msa2 = chain_msa_rows(S, nb, st);
         const DCPack *hp = S.ch_packs.p;
         const uint64_t *hmo = S.ch_msa_off.p;
         DVPack *v2 = S.vh_packs.need_geo(nb);
@@ -1484,7 +1507,7 @@ static void vote_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vector<
         char *hc = S.vh_cons.need_geo(cols2 + 16);
         CK(cudaMemcpyAsync(v2, S.v_packs.p, nb * sizeof(DVPack), cudaMemcpyDeviceToHost, st));
         if (cols2) CK(cudaMemcpyAsync(hc, S.v_cons.p, cols2, cudaMemcpyDeviceToHost, st));
-        slot_wait(S);
+        slot_wait(S, st);
         S.st.h2d_bytes += (int64_t)(nb * sizeof(DVPack));
         S.st.d2h_bytes += (int64_t)(nb * sizeof(DVPack) + cols2);
         (void)msa2;

@@ -229,9 +229,14 @@ __device__ __forceinline__ void ps_align_job(const PoaSJob &J, const uint8_t *__
     constexpr int e8 = 8 * SE;
     // 32-bit shared-space addresses (one register each, no generic-address arithmetic in the row loop)
     const ps_saddr dyn_s = (ps_saddr)__cvta_generic_to_shared(s_dyn);
-    const ps_saddr prof_s = dyn_s + (uint32_t)((wid * PS_NLET * 32 + lane) * 16);             // + letter*512
-    const ps_saddr ring_s = dyn_s + (uint32_t)((NW * PS_NLET * 32 + wid * K * 64 + lane) * 16);  // + idx*1024 (F +512)
-    const ps_saddr hring_s = dyn_s + (uint32_t)(NW * (PS_NLET * 32 + K * 64) * 16 + wid * 32);   // + idx*4
+    ps_saddr prof_s = dyn_s + (uint32_t)((wid * PS_NLET * 32 + lane) * 16);             // + letter*512
+    ps_saddr ring_s = dyn_s + (uint32_t)((NW * PS_NLET * 32 + wid * K * 64 + lane) * 16);  // + idx*1024 (F +512)
+    ps_saddr hring_s = dyn_s + (uint32_t)(NW * (PS_NLET * 32 + K * 64) * 16 + wid * 32);   // + idx*4
+#ifndef CUDA_EMU
+    // keep the three addresses in registers: left to itself the compiler re-derives them from %tid / %ntid / K in every
+    // row and for every predecessor (some thirty instructions per row)
+    asm volatile("" : "+r"(prof_s), "+r"(ring_s), "+r"(hring_s));
+#endif
     {
         const int n = J.n, nst = J.n_strips;
         uint32_t *hf = arena + J.hf_off;  // word offsets below are relative to hf (a job's region is far below 16 GB)
@@ -290,12 +295,19 @@ __device__ __forceinline__ void ps_align_job(const PoaSJob &J, const uint8_t *__
                 __syncwarp();
                 // codes of row r: tile (r-1)/8, inside it [strip][lane][row in tile][4 words]
                 uint32_t *cd_w = cd + ((size_t)t * 32 + lane) * 32;
-                const bool has_left = t > 0, has_right = t + 1 < nst;
-                const bool left_smem = pos > 0, right_smem = pos + 1 < NW;
-                const ps_saddr mb_in = (ps_saddr)__cvta_generic_to_shared(&s_mb[left_smem ? pos - 1 : 0][0]);
-                const ps_saddr mb_out = (ps_saddr)__cvta_generic_to_shared(&s_mb[pos][0]);
-                const ps_saddr done_in = (ps_saddr)__cvta_generic_to_shared(&s_done[pos]);
-                const ps_saddr done_out = (ps_saddr)__cvta_generic_to_shared(&s_done[right_smem ? pos + 1 : pos]);
+                // where this strip stands (bit 0: a strip on its left, bit 1: that one runs in this pass, bit 2: a strip on
+                // its right, bit 3: that one runs in this pass) and its mailbox addresses — opaque to the compiler, which
+                // would otherwise re-derive all of them from %tid / %ntid in every row
+                uint32_t where = (t > 0 ? 1u : 0u) | (pos > 0 ? 2u : 0u) | (t + 1 < nst ? 4u : 0u) | (pos + 1 < NW ? 8u : 0u);
+                ps_saddr mb_in = (ps_saddr)__cvta_generic_to_shared(&s_mb[pos > 0 ? pos - 1 : 0][0]);
+                ps_saddr mb_out = (ps_saddr)__cvta_generic_to_shared(&s_mb[pos][0]);
+                ps_saddr done_in = (ps_saddr)__cvta_generic_to_shared(&s_done[pos]);
+                ps_saddr done_out = (ps_saddr)__cvta_generic_to_shared(&s_done[pos + 1 < NW ? pos + 1 : pos]);
+#ifndef CUDA_EMU
+                asm volatile("" : "+r"(where), "+r"(mb_in), "+r"(mb_out), "+r"(done_in), "+r"(done_out));
+#endif
+                const bool has_left = (where & 1u) != 0u, left_smem = (where & 2u) != 0u;
+                const bool has_right = (where & 4u) != 0u, right_smem = (where & 8u) != 0u;
                 const int lane_e8 = lane * e8;
                 int cdone = 0;  // rows the right neighbour is known to have consumed
                 int bestv = 0, bestr = 0;
@@ -555,20 +567,35 @@ __device__ __forceinline__ int ps_traceback_warp(const PoaSJob &J, const int4 b,
     const int32_t *order = (J.order_off != ~0ull) ? pool + J.order_off : nullptr;
     int c_tile = -1, c_grp = -1, r_tile = -1;
     uint32_t cw = 0u, rw = 0u;
+    // The walk goes up and to the left, two to three graph rows per query column, so it leaves a tile after two or three
+    // steps, nearly always into the tile above, to the left or above-left.  Those three tiles (and the row records of the
+    // tile row above) are requested when a tile is entered and sit in registers by the time the walk gets there: the
+    // latency of the dependent load is paid once per far jump instead of once per tile.  Tiles further ahead are pulled
+    // into L2 (the codes were streamed out by the DP and are long gone from it).
+    uint32_t n_up = 0u, n_left = 0u, n_ul = 0u, n_rw = 0u;
+    auto tile_word = [&](int tile, int grp) -> uint32_t {
+        return cd[((size_t)tile * nst + (grp >> 5)) * 1024 + (size_t)(grp & 31) * 32 + lane];
+    };
+    auto rec_tile_word = [&](int tile) -> uint32_t {
+        const int rr = tile * 8 + 1 + (lane >> 2);
+        return rr <= n ? recs32[4 * (size_t)rr + (lane & 3)] : 0u;
+    };
     auto code_at = [&](int row, int col) -> uint32_t {  // row >= 1, col >= 1
         const int tile = (row - 1) >> 3, jj = col - 1, grp = jj >> 3;
         if (tile != c_tile || grp != c_grp) {
-            cw = cd[((size_t)tile * nst + (grp >> 5)) * 1024 + (size_t)(grp & 31) * 32 + lane];
+            const int dt = c_tile - tile, dg = c_grp - grp;
+            if (c_tile >= 0 && dt == 1 && dg == 0) cw = n_up;
+            else if (c_tile >= 0 && dt == 0 && dg == 1) cw = n_left;
+            else if (c_tile >= 0 && dt == 1 && dg == 1) cw = n_ul;
+            else cw = tile_word(tile, grp);
             c_tile = tile;
             c_grp = grp;
-            // The walk goes up and to the left, about two to three graph rows per query column, and every new tile costs
-            // a DRAM latency (the codes were streamed out by the DP and are long gone from L2): 24 lanes ask L2 for the
-            // tiles the path is likely to enter next — eight tile rows upwards in this and the next two tile columns,
-            // shifted by the path's slope — so that the dependent loads of the next steps hit L2.
+            if (tile > 0) n_up = tile_word(tile - 1, grp);
+            if (grp > 0) n_left = tile_word(tile, grp - 1);
+            if (tile > 0 && grp > 0) n_ul = tile_word(tile - 1, grp - 1);
             if (lane < 24) {
-                const int dc = lane >> 3, pt = tile - (lane & 7) - 2 * dc, pg = grp - dc;
-                if (pt >= 0 && pg >= 0 && (dc | (lane & 7)) != 0)
-                    ps_prefetch_l2(cd + ((size_t)pt * nst + (pg >> 5)) * 1024 + (size_t)(pg & 31) * 32);
+                const int dc = lane >> 3, pt = tile - 2 - (lane & 7) - 2 * dc, pg = grp - dc;
+                if (pt >= 0 && pg >= 0) ps_prefetch_l2(cd + ((size_t)pt * nst + (pg >> 5)) * 1024 + (size_t)(pg & 31) * 32);
             }
         }
         const uint32_t wv = __shfl_sync(0xffffffffu, cw, ((row - 1) & 7) * 4 + (jj & 3));
@@ -577,10 +604,10 @@ __device__ __forceinline__ int ps_traceback_warp(const PoaSJob &J, const int4 b,
     auto rec_word = [&](int row, int k) -> uint32_t {  // word k of the record of row >= 1
         const int tile = (row - 1) >> 3;
         if (tile != r_tile) {
-            const int rr = tile * 8 + 1 + (lane >> 2);
-            rw = rr <= n ? recs32[4 * (size_t)rr + (lane & 3)] : 0u;
+            rw = (r_tile >= 0 && tile == r_tile - 1) ? n_rw : rec_tile_word(tile);
             r_tile = tile;
-            if (lane >= 1 && lane <= 4 && tile - lane >= 0) ps_prefetch_l2(recs32 + 4 * ((size_t)(tile - lane) * 8 + 1));
+            if (tile > 0) n_rw = rec_tile_word(tile - 1);
+            if (lane >= 2 && lane <= 5 && tile - lane >= 0) ps_prefetch_l2(recs32 + 4 * ((size_t)(tile - lane) * 8 + 1));
         }
         return __shfl_sync(0xffffffffu, rw, ((row - 1) & 7) * 4 + k);
     };

@@ -207,3 +207,31 @@ def test_poa_host_sort_and_mirror_demotion(ctx, ref, opt, val):
         assert np.array_equal(a, b), "alignment %d differs" % i
     assert rows == erows
     check_correct(out, ref.correct_reads(rs.bases, rs.quals, rs.offsets, cl.as_dict(), min_reads=5, n_threads=1))
+
+
+# ---- MSA post-processing on the GPU (poa_vote.cuh) against the host pipeline and the reference
+@pytest.mark.parametrize("quals", ["random", "constant"])
+def test_correct_reads_device_vote_equals_host_vote_and_reference(ctx, ref, quals):
+    """fix_msa_ends / column vote / read correction / consensus as kernels (option poa_device_vote, the default) give the
+    bytes of the host pipeline (poa_device_vote=0) and of the unmodified reference; constant qualities make every mean
+    error a table entry or a sum of equal terms — the columns whose quality symbol the device hands to the host's log10;
+    ragged read lengths put short, badly aligned read ends into the MSAs (fix_msa_ends trims them)"""
+    rs = synth.generate(seed=23, n_genes=5, reads_per_tx=14, len_mean=700.0, len_sd=250.0, len_min=200, len_max=1500,
+                        p_flip=0.0, shuffle=False, p_sub=0.05, p_ins=0.04, p_del=0.04)
+    if quals == "constant":
+        rs.quals[:] = ord("5")
+    # clusters = the genes (14 reads each) with reads in length-descending order, one cluster too small to correct
+    lens = rs.lengths()
+    order = np.concatenate([np.arange(g * 14, (g + 1) * 14)[np.argsort(-lens[g * 14:(g + 1) * 14], kind="stable")] for g in range(5)])
+    rs = rs.take(order)
+    cl = clusters_of([14, 14, 14, 14, 10, 4])
+    exp = ref.correct_reads(rs.bases, rs.quals, rs.offsets, cl.as_dict(), min_reads=5, n_threads=1)
+    outs = {}
+    for vote in (1, 0):
+        ctx.set_option("poa_device_vote", vote)
+        try:
+            outs[vote] = ctx.correct_reads(rs.bases, rs.quals, rs.offsets, cl, min_reads=5)
+        finally:
+            ctx.set_option("poa_device_vote", 1)
+        check_correct(outs[vote], exp)
+    assert outs[0] == outs[1]
