@@ -69,8 +69,7 @@ struct DCSeq {             // one per read of a pack (host-written once)
 // entry, DC_MORE in the high half = the list is longer than two entries (walk the linked list in global memory).
 constexpr uint32_t DC_NONE = 0xffffu, DC_MORE = 0xfffeu;
 constexpr int DC_THREADS = 128;    // one CTA per pack
-constexpr int DC_SP_CAP = 2048;    // pending entries of the serial pass kept in shared memory (beyond: DGView::pending)
-constexpr int DC_SS_CAP = 1024;    // DFS frames of the serial pass kept in shared memory (beyond: DGView::stack)
+constexpr int DC_NDEF = 256;       // roots of blocks the parallel pass could not hold (more: every block is redone serially)
 constexpr int DC_TP = 16, DC_TF = 8;  // per-thread pending entries / DFS frames of the parallel pass
 constexpr int DC_MAXT = PS_MAXW * 32; // threads of the widest CTA
 
@@ -79,23 +78,27 @@ __host__ __device__ __forceinline__ uint32_t dc_rec_push(uint32_t w, uint32_t id
     if ((w >> 16) == DC_NONE) return (w & 0xffffu) | (id << 16);
     return (w & 0xffffu) | (DC_MORE << 16);
 }
-// shared-memory bytes of the sort for graphs of at most cap_n nodes: label + rank (16 bit each), mark/check byte, spill
-// flag bits, and the DFS stacks (per-thread ones of the parallel pass; the serial pass of oversized blocks reuses them)
-__host__ __device__ __forceinline__ size_t dc_stack_bytes() {
-    const size_t per_thread = (size_t)DC_MAXT * (DC_TP * 2 + DC_TF * 4);
-    const size_t serial = (size_t)DC_SP_CAP * 2 + (size_t)DC_SS_CAP * 6;
-    return (per_thread > serial ? per_thread : serial) + 1024 * 2;  // + list of deferred blocks
+// shared-memory bytes of the sort for graphs of at most cap_n nodes in a CTA of nt threads: label + rank (16 bit each),
+// mark/check byte, spill flag bits, and the DFS stacks — per-thread ones for the parallel pass; the serial pass of
+// oversized blocks reuses the area (its capacities follow from the area's size; beyond them it works in DGView::pending /
+// DGView::stack) — plus the list of deferred blocks
+__host__ __device__ __forceinline__ size_t dc_stack_area(int nt) {
+    const size_t a = (size_t)nt * (DC_TP * 2 + DC_TF * 4);
+    return a < 4096 ? 4096 : a;
 }
-__host__ __device__ __forceinline__ size_t dc_sort_smem(int cap_n) {
+__host__ __device__ __forceinline__ int dc_serial_pcap(int nt) { return (int)(dc_stack_area(nt) / 5) & ~1; }   // 2-byte entries
+__host__ __device__ __forceinline__ int dc_serial_fcap(int nt) { return (int)(dc_stack_area(nt) / 10) & ~1; }  // 6-byte frames
+__host__ __device__ __forceinline__ size_t dc_stack_bytes(int nt) { return dc_stack_area(nt) + (size_t)DC_NDEF * 2; }
+__host__ __device__ __forceinline__ size_t dc_sort_smem(int cap_n, int nt) {
     const size_t even = ((size_t)cap_n + 3) & ~(size_t)3;
-    return even * 2 + even * 2 + even + ((size_t)(cap_n + 1 + 31) / 32 + 1) * 4 + dc_stack_bytes() + 64;
+    return even * 2 + even * 2 + even + ((size_t)(cap_n + 1 + 31) / 32 + 1) * 4 + dc_stack_bytes(nt) + 64;
 }
 // largest graph whose sort fits `bytes` of shared memory (node ids must also fit the 16-bit records)
-__host__ __device__ __forceinline__ int dc_sort_cap(size_t bytes) {
+__host__ __device__ __forceinline__ int dc_sort_cap(size_t bytes, int nt) {
     int lo = 0, hi = 0xfff0;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (dc_sort_smem(mid) <= bytes) lo = mid;
+        if (dc_sort_smem(mid, nt) <= bytes) lo = mid;
         else hi = mid - 1;
     }
     return lo;
@@ -288,9 +291,9 @@ struct DCSort {
     uint8_t *mc;       // [cap] mark (bits 0-1) | check (bit 2)
     uint32_t *flag;    // spill flags of rows 0..n, one bit each
     unsigned char *stacks;  // DFS stacks: per thread [DC_TP pending | DC_TF frames], or the serial pass' big ones
-    uint16_t *deferred;     // [1024] roots of blocks the parallel pass could not hold
+    uint16_t *deferred;     // [DC_NDEF] roots of blocks the parallel pass could not hold
 };
-__device__ __forceinline__ DCSort dc_sort_view(unsigned char *base, int cap_n) {
+__device__ __forceinline__ DCSort dc_sort_view(unsigned char *base, int cap_n, int nt) {
     const size_t even = ((size_t)cap_n + 3) & ~(size_t)3;
     DCSort s;
     s.label = reinterpret_cast<uint16_t *>(base);
@@ -300,9 +303,9 @@ __device__ __forceinline__ DCSort dc_sort_view(unsigned char *base, int cap_n) {
     s.flag = reinterpret_cast<uint32_t *>(base);
     base += ((size_t)(cap_n + 1 + 31) / 32 + 1) * 4;
     s.stacks = base;
-    base += dc_stack_bytes() - 2048;
+    base += dc_stack_area(nt);
     s.deferred = reinterpret_cast<uint16_t *>(base);
-    base += 2048;
+    base += (size_t)DC_NDEF * 2;
     s.mc = base;
     return s;
 }
@@ -501,7 +504,7 @@ __device__ __forceinline__ void dc_sort_blocks(DGView &g, DCSort &s, int n) {
             const int first = (int)s.rank[i];
             if (!dc_block_dfs(g, s, i, first, pend, sv, sb, nullptr, DC_TP, DC_TF, false)) {
                 const int k = atomicAdd(&s_ndef, 1);
-                if (k < 1024) s.deferred[k] = (uint16_t)i;
+                if (k < DC_NDEF) s.deferred[k] = (uint16_t)i;
                 s.rank[i] = (uint16_t)first;  // (the pass may have overwritten it)
             }
         }
@@ -510,8 +513,8 @@ __device__ __forceinline__ void dc_sort_blocks(DGView &g, DCSort &s, int n) {
     const int ndef = s_ndef;
     if (ndef) {
         // blocks that did not fit a thread's stacks: undo what their passes left, then one thread redoes them with the
-        // big stacks.  More than 1024 such blocks (never seen): every block is redone.
-        const bool all = ndef > 1024;
+        // big stacks.  More than DC_NDEF such blocks (never seen): every block is redone.
+        const bool all = ndef > DC_NDEF;
         for (int v = tid; v < n; v += nt) {
             bool redo = all;
             if (!all)
@@ -520,9 +523,10 @@ __device__ __forceinline__ void dc_sort_blocks(DGView &g, DCSort &s, int n) {
         }
         __syncthreads();
         if (tid == 0) {
+            const int spc = dc_serial_pcap(nt), ssc = dc_serial_fcap(nt);
             uint16_t *pend = reinterpret_cast<uint16_t *>(s.stacks);
-            uint16_t *sv = pend + DC_SP_CAP;
-            uint32_t *sb = reinterpret_cast<uint32_t *>(sv + DC_SS_CAP);
+            uint16_t *sv = pend + spc;
+            uint32_t *sb = reinterpret_cast<uint32_t *>(sv + ssc);
             if (all) {
                 // positions: recount from the labels (rank entries of redone non-roots are gone)
                 int at = 0;
@@ -530,13 +534,13 @@ __device__ __forceinline__ void dc_sort_blocks(DGView &g, DCSort &s, int n) {
                     if ((int)s.label[i] != i) continue;
                     int c = 0;
                     for (int v = i; v < n; ++v) c += (int)s.label[v] == i;
-                    dc_block_dfs(g, s, i, at, pend, sv, nullptr, sb, DC_SP_CAP, DC_SS_CAP, true);
+                    dc_block_dfs(g, s, i, at, pend, sv, nullptr, sb, spc, ssc, true);
                     at += c;
                 }
             } else {
                 for (int k = 0; k < ndef; ++k) {
                     const int i = (int)s.deferred[k];
-                    dc_block_dfs(g, s, i, (int)s.rank[i], pend, sv, nullptr, sb, DC_SP_CAP, DC_SS_CAP, true);
+                    dc_block_dfs(g, s, i, (int)s.rank[i], pend, sv, nullptr, sb, spc, ssc, true);
                 }
             }
         }
@@ -586,7 +590,7 @@ __device__ __forceinline__ void dc_step_cta(DCPack &P, const DCSeq *__restrict__
     const bool want_recs = step < P.n_seq;
     int n_spill = 0;
     if (status == DC_OK && in_smem) {
-        DCSort s = dc_sort_view(dyn, smem_cap_n);
+        DCSort s = dc_sort_view(dyn, smem_cap_n, nt);
         dc_sort_blocks(g, s, n);
         tph[1] += dc_clock() - tc1;  // sort
         if (want_recs) {

@@ -330,6 +330,8 @@ static PoaState &pstate(rtl_ctx *ctx) {
         CK(cudaFuncSetAttribute(k_poa_chain<5, -4, -8, -6, 192, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CK(cudaFuncSetAttribute(k_poa_chain<5, -4, -8, -6, 192, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CK(cudaFuncSetAttribute(k_poa_chain<5, -4, -8, -6, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(k_poa_chain<5, -4, -8, -6, 128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(k_poa_chain<5, -4, -8, -6, 96, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         P.n_threads = host_threads();
         if (const char *tf = getenv("RTL_TRACE_FILE")) P.trace = fopen(tf, "w");
         CK(cudaEventCreate(&P.ev_ref));
@@ -386,6 +388,15 @@ static const uint8_t *letter_codes() {
 // strip kernel: warps per CTA = strips per pass, passes balanced (9 strips -> 2 passes of 5 and 4, not 8 and 1)
 static int strip_warps(int nst) {
     const int n_pass = (nst + PS_MAXW - 1) / PS_MAXW;
+    return (nst + n_pass - 1) / n_pass;
+}
+// Device-resident chains, narrow CTAs: a pack's CTA spends a third of its time in phases that occupy one warp (graph
+// update, traceback) while its other warps wait, so CTAs of at most four warps — reads of more than four strips run in
+// balanced passes, 6 strips as 3 + 3 — leave fewer warps idle and twice as many packs share an SM.
+static int chain_warps(int nst) {
+    static const bool narrow = getenv("RATTLE_B200_NARROW") != nullptr && atoi(getenv("RATTLE_B200_NARROW")) != 0;
+    if (!narrow) return strip_warps(nst);
+    const int n_pass = (nst + 3) / 4;
     return (nst + n_pass - 1) / n_pass;
 }
 // rows of the shared-memory ring for a CTA of nw warps: 6 where the register file limits the CTAs per SM anyway,
@@ -956,7 +967,7 @@ static ChainRun chain_run(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vect
             w += (double)l * sum;  // read x (nodes so far, at most the bases so far)
             sum += l;
         }
-        ents[i] = Ent{strip_warps(sizes[i].max_nst), w, (int32_t)i};
+        ents[i] = Ent{chain_warps(sizes[i].max_nst), w, (int32_t)i};
     }
     std::sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) {
         if (a.key != b.key) return a.key > b.key;
@@ -1027,12 +1038,15 @@ static ChainRun chain_run(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vect
         const bool five = nw <= 6 && getenv("RATTLE_B200_CTAS5") != nullptr;
         // 8-warp CTAs: four per SM at 64 registers (8 bytes of spill) beat three at 80: +8 % on 2 kb reads (config 4)
         const bool four8 = nw == 8 && getenv("RATTLE_B200_CTAS3") == nullptr;
-        const size_t budget = five ? (size_t)43 * 1024 : (four8 ? (size_t)54 * 1024 : (four ? (size_t)54 * 1024 : (size_t)72 * 1024));
+        const bool narrow = getenv("RATTLE_B200_NARROW") != nullptr && atoi(getenv("RATTLE_B200_NARROW")) != 0 && nw <= 4;
+        // narrow CTAs: 8 per SM for up to 3 warps (26 KB each), 6 per SM for 4 warps (35 KB)
+        const size_t budget = narrow ? (nw <= 3 ? (size_t)26 * 1024 : (size_t)35 * 1024)
+                                     : (five ? (size_t)43 * 1024 : (four8 ? (size_t)54 * 1024 : (four ? (size_t)54 * 1024 : (size_t)72 * 1024)));
         int K = strip_ring_rows(nw);
         while (K > 3 && ps_smem_bytes(nw, K) > budget) --K;
         const size_t smem = std::max(ps_smem_bytes(nw, K), budget);
-        const int smem_cap_n = dc_sort_cap(smem);
-        auto kern = nw == 8 ? (four8 ? k_poa_chain<5, -4, -8, -6, 256, 4> : k_poa_chain<5, -4, -8, -6, 256, 3>)
+        const int smem_cap_n = dc_sort_cap(smem, nw * 32);
+        auto kern = narrow ? (nw <= 3 ? k_poa_chain<5, -4, -8, -6, 96, 8> : k_poa_chain<5, -4, -8, -6, 128, 6>) : nw == 8 ? (four8 ? k_poa_chain<5, -4, -8, -6, 256, 4> : k_poa_chain<5, -4, -8, -6, 256, 3>)
                             : (!four ? k_poa_chain<5, -4, -8, -6, 256, 3>
                                      : (nw == 7 ? k_poa_chain<5, -4, -8, -6, 224, 4>
                                                 : (five ? k_poa_chain<5, -4, -8, -6, 192, 5> : k_poa_chain<5, -4, -8, -6, 192, 4>)));

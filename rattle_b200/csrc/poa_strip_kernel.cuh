@@ -567,35 +567,20 @@ __device__ __forceinline__ int ps_traceback_warp(const PoaSJob &J, const int4 b,
     const int32_t *order = (J.order_off != ~0ull) ? pool + J.order_off : nullptr;
     int c_tile = -1, c_grp = -1, r_tile = -1;
     uint32_t cw = 0u, rw = 0u;
-    // The walk goes up and to the left, two to three graph rows per query column, so it leaves a tile after two or three
-    // steps, nearly always into the tile above, to the left or above-left.  Those three tiles (and the row records of the
-    // tile row above) are requested when a tile is entered and sit in registers by the time the walk gets there: the
-    // latency of the dependent load is paid once per far jump instead of once per tile.  Tiles further ahead are pulled
-    // into L2 (the codes were streamed out by the DP and are long gone from it).
-    uint32_t n_up = 0u, n_left = 0u, n_ul = 0u, n_rw = 0u;
-    auto tile_word = [&](int tile, int grp) -> uint32_t {
-        return cd[((size_t)tile * nst + (grp >> 5)) * 1024 + (size_t)(grp & 31) * 32 + lane];
-    };
-    auto rec_tile_word = [&](int tile) -> uint32_t {
-        const int rr = tile * 8 + 1 + (lane >> 2);
-        return rr <= n ? recs32[4 * (size_t)rr + (lane & 3)] : 0u;
-    };
     auto code_at = [&](int row, int col) -> uint32_t {  // row >= 1, col >= 1
         const int tile = (row - 1) >> 3, jj = col - 1, grp = jj >> 3;
         if (tile != c_tile || grp != c_grp) {
-            const int dt = c_tile - tile, dg = c_grp - grp;
-            if (c_tile >= 0 && dt == 1 && dg == 0) cw = n_up;
-            else if (c_tile >= 0 && dt == 0 && dg == 1) cw = n_left;
-            else if (c_tile >= 0 && dt == 1 && dg == 1) cw = n_ul;
-            else cw = tile_word(tile, grp);
+            cw = cd[((size_t)tile * nst + (grp >> 5)) * 1024 + (size_t)(grp & 31) * 32 + lane];
             c_tile = tile;
             c_grp = grp;
-            if (tile > 0) n_up = tile_word(tile - 1, grp);
-            if (grp > 0) n_left = tile_word(tile, grp - 1);
-            if (tile > 0 && grp > 0) n_ul = tile_word(tile - 1, grp - 1);
+            // The walk goes up and to the left, about two to three graph rows per query column, and every new tile costs
+            // a DRAM latency (the codes were streamed out by the DP and are long gone from L2): 24 lanes ask L2 for the
+            // tiles the path is likely to enter next — eight tile rows upwards in this and the next two tile columns,
+            // shifted by the path's slope — so that the dependent loads of the next steps hit L2.
             if (lane < 24) {
-                const int dc = lane >> 3, pt = tile - 2 - (lane & 7) - 2 * dc, pg = grp - dc;
-                if (pt >= 0 && pg >= 0) ps_prefetch_l2(cd + ((size_t)pt * nst + (pg >> 5)) * 1024 + (size_t)(pg & 31) * 32);
+                const int dc = lane >> 3, pt = tile - (lane & 7) - 2 * dc, pg = grp - dc;
+                if (pt >= 0 && pg >= 0 && (dc | (lane & 7)) != 0)
+                    ps_prefetch_l2(cd + ((size_t)pt * nst + (pg >> 5)) * 1024 + (size_t)(pg & 31) * 32);
             }
         }
         const uint32_t wv = __shfl_sync(0xffffffffu, cw, ((row - 1) & 7) * 4 + (jj & 3));
@@ -604,10 +589,10 @@ __device__ __forceinline__ int ps_traceback_warp(const PoaSJob &J, const int4 b,
     auto rec_word = [&](int row, int k) -> uint32_t {  // word k of the record of row >= 1
         const int tile = (row - 1) >> 3;
         if (tile != r_tile) {
-            rw = (r_tile >= 0 && tile == r_tile - 1) ? n_rw : rec_tile_word(tile);
+            const int rr = tile * 8 + 1 + (lane >> 2);
+            rw = rr <= n ? recs32[4 * (size_t)rr + (lane & 3)] : 0u;
             r_tile = tile;
-            if (tile > 0) n_rw = rec_tile_word(tile - 1);
-            if (lane >= 2 && lane <= 5 && tile - lane >= 0) ps_prefetch_l2(recs32 + 4 * ((size_t)(tile - lane) * 8 + 1));
+            if (lane >= 1 && lane <= 4 && tile - lane >= 0) ps_prefetch_l2(recs32 + 4 * ((size_t)(tile - lane) * 8 + 1));
         }
         return __shfl_sync(0xffffffffu, rw, ((row - 1) & 7) * 4 + k);
     };

@@ -82,7 +82,7 @@ int main(int argc, char **argv) {
         const int K = fi % 2 ? 5 : 6;  // both ring depths
         const int32_t list0 = 0;
         unsigned counter = 0;
-        const int smem_cap_n = sort_in_smem ? dc_sort_cap(72 * 1024) : 0;
+        const int smem_cap_n = sort_in_smem ? dc_sort_cap(72 * 1024, nw * 32) : 0;
         emu::launch(1, (unsigned)nw * 32, [&]() {
             k_poa_chain<5, -4, -8, -6, 256, 3>(&P, &list0, 1, sq.data(), pool.data(), q.data(), reinterpret_cast<uint4 *>(rec.data()),
                                        preds.data(), spill_rows.data(), aln.data(), path.data(), qnode.data(), arena.data(),

@@ -16,7 +16,7 @@
 using namespace rtl;
 
 static void sort_kernel(DGView g, int n, int cap) {
-    DCSort s = dc_sort_view(emu::g_smem, cap);
+    DCSort s = dc_sort_view(emu::g_smem, cap, (int)blockDim.x);
     dc_sort_blocks(g, s, n);
 }
 
@@ -38,7 +38,7 @@ int main(int argc, char **argv) {
         }
         PoaGraph g;
         const int cap_n = 12000, cap_e = 3 * cap_n, cap_a = 4 * cap_n;
-        if (dc_sort_smem(cap_n) > sizeof(emu::g_smem)) return 2;
+        if (dc_sort_smem(cap_n, (int)nt) > sizeof(emu::g_smem)) return 2;
         std::vector<int32_t> block(dg_words(cap_n, cap_e, cap_a));
         DGView dv = dg_view(block.data(), cap_n, cap_e, cap_a);
         for (int i = 0; i < n; ++i) {
