@@ -219,7 +219,8 @@ def workload_config(args, n_reads, genes, world):
                             "; = the 1 M reads of BASELINE.json's metric" if n_reads == 1000000 else ""),
             "n_reads": int(n_reads), "kmer_size": 10, "strands": 2, "l2": "inputs larger than L2 (k-mer lists + "
             "bitvectors of the workload exceed 126 MB); no explicit flush",
-            "parallelism": "wave pairs sharded x%d + min-allreduce (cluster), clusters round-robin x%d (correct)" % (world, world)}
+            "parallelism": "reads block-sharded x%d for k-mer extraction + broadcast of the blocks, wave pairs sharded x%d + "
+                           "min-allreduce of the decisions (cluster), clusters round-robin x%d (correct)" % (world, world, world)}
 
 
 def main():
@@ -249,7 +250,7 @@ def main():
     import torch
     import torch.distributed as dist
     import rattle_b200
-    from rattle_b200.dist import make_allreduce_callback, shard_clusters
+    from rattle_b200.dist import make_allreduce_callback, make_broadcast_callback, shard_clusters
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -266,6 +267,7 @@ def main():
     allreduce_cb = make_allreduce_callback(stream.cuda_stream) if world > 1 else None
     if world > 1:
         ctx.set_shard(rank, world, allreduce_cb)
+        ctx.set_broadcast(make_broadcast_callback(stream.cuda_stream))
 
     total_genes = args.genes * world
     rs = make_workload(total_genes)
@@ -356,6 +358,7 @@ def main():
     if world > 1 and not args.no_check:
         if rank == 0:
             ctx.set_shard(0, 1, None)
+            ctx.set_broadcast(None)
             t0 = time.perf_counter()
             cl1 = ctx.cluster_reads(bases_np, rs.offsets, **CLUSTER_KW)
             ref_d = {"clusters_sha256": cluster_digest(cl1)}

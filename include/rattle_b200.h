@@ -129,6 +129,14 @@ int rtl_cluster_resident(rtl_ctx *ctx, int kmer_size, double t_s, double t_v, do
 typedef int (*rtl_allreduce_min_fn)(void *user, void *device_ptr_u32, int64_t count);
 int rtl_set_shard(rtl_ctx *ctx, int rank, int world, rtl_allreduce_min_fn fn, void *user);
 
+/* Sharded k-mer extraction (reads block-partitioned over the GPUs, the k-mer lists and bitvectors
+ * gathered so that every GPU can hold any representative).  With a broadcast callback set (and world > 1), rank r
+ * extracts only reads [r*n/world, (r+1)*n/world) and the ranks exchange their slices of the k-mer lists, bitvectors and
+ * popcounts: the callback copies `bytes` at `device_ptr` from rank `root` to the same address range of every other rank
+ * (ncclBroadcast in rattle_b200/dist.py), ordered against the ctx stream.  Without it every rank extracts every read. */
+typedef int (*rtl_broadcast_fn)(void *user, void *device_ptr, int64_t bytes, int root);
+int rtl_set_broadcast(rtl_ctx *ctx, rtl_broadcast_fn fn, void *user);
+
 /* Function-granularity entry points (same data layout as the kernels use). */
 /* k-mer lists: for read i the len_i-k entries start at offsets[i]-i*k; sorted by (hash,pos). rev_* and bv_rev
  * may be NULL when both_strands=0. bv_*: n_reads x 64 uint64. */

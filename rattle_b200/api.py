@@ -34,11 +34,12 @@ class Stats(ctypes.Structure):
 
 
 ALLREDUCE_FN = ctypes.CFUNCTYPE(c_i, c_p, c_p, c_i64)
+BROADCAST_FN = ctypes.CFUNCTYPE(c_i, c_p, c_p, c_i64, c_i)
 
 # every symbol include/rattle_b200.h declares (tests/test_boundary.py checks the header against this list)
 SYMBOLS = ["rtl_init", "rtl_destroy", "rtl_last_error", "rtl_set_option", "rtl_set_stream", "rtl_get_stats", "rtl_cluster_reads",
            "rtl_cluster_reads_batched",
-           "rtl_reads_upload", "rtl_cluster_resident", "rtl_set_shard", "rtl_extract_kmers", "rtl_bv_scan",
+           "rtl_reads_upload", "rtl_cluster_resident", "rtl_set_shard", "rtl_set_broadcast", "rtl_extract_kmers", "rtl_bv_scan",
            "rtl_pair_similarity", "rtl_poa_msa", "rtl_correct_reads", "rtl_set_labels", "rtl_set_cluster_ids", "rtl_hps_encode", "rtl_hps_decode"]
 
 _lib = None
@@ -81,6 +82,8 @@ def load_library():
     L.rtl_cluster_resident.argtypes = [c_p, c_i, c_d, c_d, c_d, c_d, c_d, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p]
     L.rtl_set_shard.restype = c_i
     L.rtl_set_shard.argtypes = [c_p, c_i, c_i, ALLREDUCE_FN, c_p]
+    L.rtl_set_broadcast.restype = c_i
+    L.rtl_set_broadcast.argtypes = [c_p, BROADCAST_FN, c_p]
     L.rtl_extract_kmers.restype = c_i
     L.rtl_extract_kmers.argtypes = [c_p, c_p, c_p, c_u32, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]
     L.rtl_set_labels.restype = c_i
@@ -202,6 +205,23 @@ class Context:
             cb = ALLREDUCE_FN(_tramp)
         self._cb = cb
         self._check(self.L.rtl_set_shard(self.h, rank, world, cb, None))
+
+    def set_broadcast(self, broadcast=None):
+        """broadcast(device_ptr:int, nbytes:int, root:int) -> 0 on success: copies nbytes at device_ptr from rank `root` to
+        every other rank (sharded k-mer extraction, rtl_set_broadcast); None = every rank extracts every read."""
+        if broadcast is None:
+            cb = ctypes.cast(None, BROADCAST_FN)
+        else:
+            def _tramp(_user, ptr, nbytes, root):
+                try:
+                    return int(broadcast(int(ptr), int(nbytes), int(root)) or 0)
+                except Exception:  # never let an exception cross the C ABI
+                    import traceback
+                    traceback.print_exc()
+                    return -1
+            cb = BROADCAST_FN(_tramp)
+        self._bcb = cb
+        self._check(self.L.rtl_set_broadcast(self.h, cb, None))
 
     # ---- hot path A
     def _cluster_out(self, n):

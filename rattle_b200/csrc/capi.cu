@@ -177,6 +177,13 @@ int rtl_set_shard(rtl_ctx *ctx, int rank, int world, rtl_allreduce_min_fn fn, vo
     return RTL_OK;
 }
 
+int rtl_set_broadcast(rtl_ctx *ctx, rtl_broadcast_fn fn, void *user) {
+    if (!ctx) return RTL_ERR_STATE;
+    ctx->broadcast = fn;
+    ctx->broadcast_user = user;
+    return RTL_OK;
+}
+
 int rtl_reads_upload(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, uint32_t n_reads) {
     return guarded(ctx, [&]() {
         cluster_upload(ctx, bases, offsets, n_reads);

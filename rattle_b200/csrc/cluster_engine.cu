@@ -173,10 +173,15 @@ void cluster_extract(rtl_ctx *ctx, int k, int both) {
     S.bv[0] = S.bvbuf.p;
     S.bv[1] = both ? S.bvbuf.p + 64 : S.bvbuf.p + (size_t)n * 64;  // (single strand: 64 words nobody reads)
     S.pc.need(n);
+    // multi-GPU with an exchange callback: this rank extracts its block of the reads, the ranks exchange their slices
+    // afterwards; otherwise every rank extracts everything
+    const bool sharded = ctx->world > 1 && ctx->broadcast != nullptr && ctx->allreduce != nullptr;
+    auto slice_lo = [&](int r) { return (uint32_t)((uint64_t)n * (uint64_t)r / (uint64_t)ctx->world); };
+    const uint32_t my_lo = sharded ? slice_lo(ctx->rank) : 0, my_hi = sharded ? slice_lo(ctx->rank + 1) : n;
     // bucket reads by padded list size
     const int n_cls = sizeof(SORT_CLASSES) / sizeof(int);
     std::vector<std::vector<uint32_t>> bucket(n_cls + 1);
-    for (uint32_t i = 0; i < n; ++i) {
+    for (uint32_t i = my_lo; i < my_hi; ++i) {
         const int nk = S.h_len[i] - k;
         int c = 0;
         while (c < n_cls && nk > SORT_CLASSES[c]) ++c;
@@ -191,8 +196,8 @@ void cluster_extract(rtl_ctx *ctx, int k, int both) {
     }
     start[n_cls + 1] = flat.size();
     S.read_list.need(n);
-    CK(cudaMemcpyAsync(S.read_list.p, flat.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    ctx->stats.h2d_bytes += (int64_t)n * 4;
+    CK(cudaMemcpyAsync(S.read_list.p, flat.data(), flat.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    ctx->stats.h2d_bytes += (int64_t)flat.size() * 4;
     S.ev.begin(EV_EXTRACT, st);
     for (int c = 0; c < n_cls; ++c) {
         const size_t cnt = start[c + 1] - start[c];
@@ -233,6 +238,29 @@ void cluster_extract(rtl_ctx *ctx, int k, int both) {
             ctx->stats.kernel_launches++;
             CK(cudaStreamSynchronize(st));  // `so` must outlive the copy
         }
+    }
+    if (sharded) {
+        // every rank's slice of the k-mer lists (read r's list starts at off[r] - k*r), bitvectors and popcounts goes to
+        // all the others; a bad base seen by one rank fails the call on every rank
+        for (int r = 0; r < ctx->world; ++r) {
+            const uint32_t lo = slice_lo(r), hi = slice_lo(r + 1);
+            if (hi == lo) continue;
+            const uint64_t k0 = S.h_off[lo] - (uint64_t)k * lo, k1 = S.h_off[hi] - (uint64_t)k * hi;
+            int rc = 0;
+            for (int s = 0; s < (both ? 2 : 1) && !rc; ++s) {
+                rc = ctx->broadcast(ctx->broadcast_user, S.kh[s].p + k0, (int64_t)((k1 - k0) * 4), r);
+                if (!rc) rc = ctx->broadcast(ctx->broadcast_user, S.kp[s].p + k0, (int64_t)((k1 - k0) * 4), r);
+            }
+            if (!rc) rc = ctx->broadcast(ctx->broadcast_user, S.bvbuf.p + (size_t)lo * S.bv_stride,
+                                         (int64_t)((size_t)(hi - lo) * S.bv_stride * 8), r);
+            if (!rc) rc = ctx->broadcast(ctx->broadcast_user, S.pc.p + lo, (int64_t)(hi - lo) * 4, r);
+            if (rc) throw CudaError("broadcast callback failed");
+        }
+        uint32_t *status = reinterpret_cast<uint32_t *>(S.flags.p + 3);
+        k_fold_input_flag<<<1, 1, 0, st>>>(S.flags.p, status);
+        if (ctx->allreduce(ctx->allreduce_user, status, 1) != 0) throw CudaError("allreduce callback failed");
+        k_unfold_input_flag<<<1, 1, 0, st>>>(S.flags.p, status);
+        ctx->stats.kernel_launches += 2;
     }
     S.ev.end(EV_EXTRACT, st);
     int *hf = S.h_flags.need(4);

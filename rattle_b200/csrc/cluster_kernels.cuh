@@ -1100,6 +1100,9 @@ __global__ void k_apply(uint32_t *best, int t0, int M, const int32_t *seed_item,
 // multi-GPU: a rank-local overflow must stop EVERY rank (the others would wait in the next exchange for ever): the flag
 // travels with the decision array as one more uint32 (0 = some rank overflowed; smaller wins in the min-reduction)
 __global__ void k_fold_status(const int *flags, uint32_t *status) { *status = flags[1] ? 0u : 0xffffffffu; }
+// sharded extraction: "some rank met a base outside ACGTU" travels as a min-reduced word (0 = error)
+__global__ void k_fold_input_flag(const int *flags, uint32_t *status) { *status = flags[0] ? 0u : 0xffffffffu; }
+__global__ void k_unfold_input_flag(int *flags, const uint32_t *status) { if (*status == 0u) flags[0] = 1; }
 
 __global__ void k_fill_u32(uint32_t *p, uint32_t v, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;

@@ -138,6 +138,8 @@ struct rtl_ctx {
     int rank = 0, world = 1;
     rtl_allreduce_min_fn allreduce = nullptr;
     void *allreduce_user = nullptr;
+    rtl_broadcast_fn broadcast = nullptr;  // sharded extraction (rtl_set_broadcast)
+    void *broadcast_user = nullptr;
     ClusterState *cl = nullptr;
     PoaState *poa = nullptr;
 };

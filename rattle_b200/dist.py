@@ -1,6 +1,7 @@
 """Multi-GPU host logic (one process per GPU, torch.distributed for the plumbing).
 
-clustering: every rank holds the whole read set (extraction is replicated), evaluates the (seed,target) pairs of each
+clustering: every rank holds the whole read set; rank r extracts the k-mers of its block of reads and the blocks are
+            exchanged (make_broadcast_callback); every rank then evaluates the (seed,target) pairs of each
             greedy wave whose target index t has t % world == rank, and the per-wave decision arrays (uint32, smaller
             wins, 0xffffffff = none) are min-reduced across ranks — the one real exchange step of the path.
 correction: independent clusters -> round-robin shards, no collective.
@@ -40,6 +41,33 @@ def make_allreduce_callback(cuda_stream, group=None):
         with torch.cuda.stream(ext):
             t = torch.as_tensor(_DevView(ptr, count), device="cuda")
             allreduce_min_u32_(t, group)
+        return 0
+    return cb
+
+
+class _DevBytes:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def make_broadcast_callback(cuda_stream, group=None):
+    """callback(ptr, nbytes, root) for Context.set_broadcast: the k-mer lists / bitvectors of rank `root`'s block of reads
+    go to every rank over NCCL (sharded extraction), enqueued on the Context's stream."""
+    import torch
+    import torch.distributed as dist
+    if not cuda_stream:
+        raise ValueError("make_broadcast_callback needs the explicit (non-default) CUDA stream the Context runs on")
+    ext = torch.cuda.ExternalStream(cuda_stream)
+    chunk = 1 << 30  # (views stay below 2^31 elements)
+
+    def cb(ptr, nbytes, root):
+        with torch.cuda.stream(ext):
+            at = 0
+            while at < nbytes:
+                n = min(chunk, nbytes - at)
+                t = torch.as_tensor(_DevBytes(ptr + at, n), device="cuda")
+                dist.broadcast(t, src=root, group=group)
+                at += n
         return 0
     return cb
 

@@ -21,10 +21,15 @@ class _DevView:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3}
 
 
+class _ByteView:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
 class ThreadRanks:
     """world contexts on device 0, one thread each; the callback min-reduces the ranks' buffers on the device"""
 
-    def __init__(self, world, options=None):
+    def __init__(self, world, options=None, broadcast=True):
         import torch
         import rattle_b200
         self.torch = torch
@@ -34,11 +39,15 @@ class ThreadRanks:
         self.streams = [torch.cuda.Stream() for _ in range(world)]
         self.ctxs = [rattle_b200.Context(0) for _ in range(world)]
         self.calls = 0
+        self.bviews = [None] * world
+        self.bcasts = 0
         for r, c in enumerate(self.ctxs):
             for k, v in (options or {}).items():
                 c.set_option(k, v)
             c.set_stream(self.streams[r].cuda_stream)
             c.set_shard(r, world, self._callback(r))
+            if broadcast:  # sharded k-mer extraction (rtl_set_broadcast); without it every rank extracts every read
+                c.set_broadcast(self._broadcast(r))
 
     def _callback(self, rank):
         torch = self.torch
@@ -58,6 +67,25 @@ class ThreadRanks:
                     v.copy_(m)
                 torch.cuda.synchronize()
                 self.calls += 1
+            self.barrier.wait()
+            return 0
+        return cb
+
+    def _broadcast(self, rank):
+        """rtl_set_broadcast's contract between threads: rank `root`'s bytes go to the same address range of the others"""
+        torch = self.torch
+
+        def cb(ptr, nbytes, root):
+            self.streams[rank].synchronize()
+            self.bviews[rank] = torch.as_tensor(_ByteView(ptr, nbytes), device="cuda")
+            self.barrier.wait()
+            if rank == 0:
+                assert len({v.numel() for v in self.bviews}) == 1, "ranks disagree on the broadcast size"
+                for r, v in enumerate(self.bviews):
+                    if r != root:
+                        v.copy_(self.bviews[root])
+                torch.cuda.synchronize()
+                self.bcasts += 1
             self.barrier.wait()
             return 0
         return cb
@@ -107,7 +135,7 @@ def test_sharded_clustering_equals_unsharded_and_oracle(ctx, orc, world, wave):
         pairs = [c.stats()["bv_pairs"] for c in ranks.ctxs]
     finally:
         ranks.close()
-    assert ranks.calls > 0
+    assert ranks.calls > 0 and ranks.bcasts > 0
     for o in outs:
         assert same(o, single)
         for k in ("main_id", "main_rev", "cl_off", "mem_id", "mem_rev"):
@@ -115,6 +143,40 @@ def test_sharded_clustering_equals_unsharded_and_oracle(ctx, orc, world, wave):
     # the ranks really split the work: nobody evaluated (nearly) all pairs
     total = ctx.stats()["bv_pairs"]
     assert max(pairs) < 0.8 * total, (pairs, total)
+
+
+def test_sharded_extraction_exchanges_the_blocks(ctx):
+    """rtl_set_broadcast: rank r extracts reads [r*n/W, (r+1)*n/W) only; after the exchange every rank holds every read's
+    k-mer lists and bitvectors, bit-identical to an unsharded extraction; without the callback the ranks extract everything
+    themselves (same result); a base outside ACGTU in ONE rank's block fails the call on EVERY rank"""
+    import rattle_b200
+    rs = synth.generate(seed=36, n_genes=11, reads_per_tx=9, len_mean=800.0, len_sd=200.0, len_min=300, len_max=1800).sorted_by_length()[0]
+    want = ctx.extract_kmers(rs.bases, rs.offsets, 10, True)
+    for bc in (True, False):
+        ranks = ThreadRanks(3, broadcast=bc)
+        try:
+            outs = ranks.run(lambda r, c: c.extract_kmers(rs.bases, rs.offsets, 10, True))
+        finally:
+            ranks.close()
+        assert (ranks.bcasts > 0) == bc
+        for o in outs:
+            for a, b in zip(o, want):
+                assert np.array_equal(a, b)
+    bad = rs.bases.copy()
+    bad[int(rs.offsets[rs.n - 2]) + 5] = ord("N")  # in the last rank's block
+    ranks = ThreadRanks(3)
+    errs = []
+
+    def attempt(r, c):
+        try:
+            c.extract_kmers(bad, rs.offsets, 10, True)
+        except rattle_b200.RattleError as e:
+            errs.append((r, e.code))
+    try:
+        ranks.run(attempt)
+    finally:
+        ranks.close()
+    assert sorted(r for r, _ in errs) == [0, 1, 2] and all(code == -2 for _, code in errs)
 
 
 def test_sharded_clustering_rna_single_strand(ctx):
