@@ -102,6 +102,13 @@ int rtl_cluster_reads(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, 
                       double repr_percentile, int is_rna, int32_t *main_id, uint8_t *main_rev, int64_t *cl_off,
                       int32_t *mem_id, uint8_t *mem_rev, int32_t *n_clusters);
 
+/* Read ingest on the GPU.  rtl_reads_upload / rtl_cluster_reads pack the uploaded reads to 2 bits per
+ * base on the device (kmer.hpp:25-31 codes; the k-mer extraction reads the packed copy) and flag bases outside A,C,G,T,U.
+ * rtl_sort_reads_by_length replaces sort_read_set (/root/reference/fasta.cpp:458-464, called at main.cpp:254 before
+ * cluster_reads): perm[i] = index of the read that comes i-th in the greedy visitation order — longest first, ties in
+ * input order (a stable sort). */
+int rtl_sort_reads_by_length(rtl_ctx *ctx, const uint64_t *offsets, uint32_t n_reads, uint32_t *perm);
+
 /* Batched cluster_reads(): the read set is the concatenation of n_seg independent read sets ("segments": reads
  * seg_off[s] .. seg_off[s+1]-1, each already in visitation order), clustered as n_seg separate cluster_reads() calls with
  * the same parameters would — the per-gene loop of `rattle cluster --iso` (/root/reference/main.cpp:281-324, call at :300)

@@ -38,7 +38,7 @@ BROADCAST_FN = ctypes.CFUNCTYPE(c_i, c_p, c_p, c_i64, c_i)
 
 # every symbol include/rattle_b200.h declares (tests/test_boundary.py checks the header against this list)
 SYMBOLS = ["rtl_init", "rtl_destroy", "rtl_last_error", "rtl_set_option", "rtl_set_stream", "rtl_get_stats", "rtl_cluster_reads",
-           "rtl_cluster_reads_batched",
+           "rtl_cluster_reads_batched", "rtl_sort_reads_by_length",
            "rtl_reads_upload", "rtl_cluster_resident", "rtl_set_shard", "rtl_set_broadcast", "rtl_extract_kmers", "rtl_bv_scan",
            "rtl_pair_similarity", "rtl_poa_msa", "rtl_correct_reads", "rtl_set_labels", "rtl_set_cluster_ids", "rtl_hps_encode", "rtl_hps_decode"]
 
@@ -76,6 +76,8 @@ def load_library():
     L.rtl_cluster_reads_batched.restype = c_i
     L.rtl_cluster_reads_batched.argtypes = [c_p, c_p, c_p, c_u32, c_p, c_u32, c_i, c_d, c_d, c_d, c_d, c_d, c_d, c_i, c_p, c_p,
                                             c_p, c_p, c_p, c_p, c_p]
+    L.rtl_sort_reads_by_length.restype = c_i
+    L.rtl_sort_reads_by_length.argtypes = [c_p, c_p, c_u32, c_p]
     L.rtl_reads_upload.restype = c_i
     L.rtl_reads_upload.argtypes = [c_p, c_p, c_p, c_u32]
     L.rtl_cluster_resident.restype = c_i
@@ -262,6 +264,14 @@ class Context:
                                                      t_s, t_v, bv_threshold, min_bv_threshold, bv_falloff, repr_percentile,
                                                      int(is_rna), *[_ptr(a) for a in out], ctypes.byref(nc), _ptr(seg_cl_off)))
         return self._pack(nc.value, out), seg_cl_off
+
+    def sort_by_length(self, offsets) -> np.ndarray:
+        """sort_read_set (fasta.cpp:458-464) on the GPU: the permutation that puts the reads into visitation order"""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        perm = np.zeros(n, np.uint32)
+        self._check(self.L.rtl_sort_reads_by_length(self.h, _ptr(offsets), n, _ptr(perm)))
+        return perm
 
     def upload(self, bases, offsets):
         bases = _bases(bases)

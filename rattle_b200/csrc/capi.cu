@@ -7,6 +7,7 @@
 void cluster_state_free(rtl_ctx *ctx);
 void cluster_upload(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, uint32_t n);
 void cluster_extract(rtl_ctx *ctx, int k, int both);
+void cluster_sort_by_length(rtl_ctx *ctx, const uint64_t *offsets, uint32_t n, uint32_t *perm);
 void cluster_run(rtl_ctx *ctx, int k, double t_s, double t_v, double bv_thr, double bv_min, double bv_falloff,
                  double repr_pct, int is_rna, int32_t *main_id, uint8_t *main_rev, int64_t *cl_off, int32_t *mem_id,
                  uint8_t *mem_rev, int32_t *n_clusters, const uint32_t *seg_off = nullptr, uint32_t n_seg = 0,
@@ -175,6 +176,14 @@ int rtl_set_shard(rtl_ctx *ctx, int rank, int world, rtl_allreduce_min_fn fn, vo
     ctx->allreduce = fn;
     ctx->allreduce_user = user;
     return RTL_OK;
+}
+
+int rtl_sort_reads_by_length(rtl_ctx *ctx, const uint64_t *offsets, uint32_t n_reads, uint32_t *perm) {
+    return guarded(ctx, [&]() {
+        ctx->stats = rtl_stats{};
+        cluster_sort_by_length(ctx, offsets, n_reads, perm);
+        return RTL_OK;
+    });
 }
 
 int rtl_set_broadcast(rtl_ctx *ctx, rtl_broadcast_fn fn, void *user) {

@@ -58,7 +58,9 @@ struct ClusterState {
     uint64_t total = 0;
     std::vector<uint64_t> h_off;
     std::vector<int32_t> h_len;
-    DevBuf<uint8_t> d_bases;
+    DevBuf<uint8_t> d_bases;    // ASCII staging of the upload
+    DevBuf<uint32_t> d_pk;      // the resident read set: 2-bit packed (k_pack_bases)
+    DevBuf<int> pack_flag;      // != 0: the upload met a base outside A,C,G,T,U
     DevBuf<uint64_t> d_off;
     DevBuf<int32_t> d_len;
     int ex_k = -1, ex_both = -1;
@@ -135,12 +137,51 @@ void cluster_upload(rtl_ctx *ctx, const char *bases, const uint64_t *offsets, ui
     CK(cudaMemcpyAsync(S.d_bases.p, bases + o0, S.total, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(S.d_off.p, S.h_off.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaEventRecord(S.up_timer.b, ctx->stream));
+    // K1: pack to 2 bits per base; everything downstream reads the packed copy
+    S.d_pk.need((S.total >> 4) + n + 2);
+    CK(cudaMemsetAsync(S.pack_flag.need(1), 0, sizeof(int), ctx->stream));
+    k_pack_bases<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(S.d_bases.p, S.d_off.p, n, S.d_pk.p, S.pack_flag.p);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
     ctx->stats.h2d_bytes += (int64_t)S.total + (int64_t)(n + 1) * 8;
     S.ex_k = -1;
     CK(cudaStreamSynchronize(ctx->stream));
     float up_ms = 0;
     CK(cudaEventElapsedTime(&up_ms, S.up_timer.a, S.up_timer.b));
     ctx->stats.upload_ms += up_ms;
+}
+
+// ------------------------------------------------------------------------------------------------ visitation order
+// sort_read_set (fasta.cpp:458-464; main.cpp:254 calls it before cluster_reads): perm[i] = index of the read that comes
+// i-th, longest first, ties in input order
+void cluster_sort_by_length(rtl_ctx *ctx, const uint64_t *offsets, uint32_t n, uint32_t *perm) {
+    if (n == 0) return;
+    if (!offsets || !perm) throw InputError("null buffers");
+    for (uint32_t i = 0; i < n; ++i)
+        if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 0x7fffffffull) throw InputError("bad read offsets");
+    cudaStream_t st = ctx->stream;
+    uint32_t n_pad = 2048;
+    while (n_pad < n) n_pad <<= 1;
+    DevBuf<uint64_t> d_off, d_keys;
+    DevBuf<uint32_t> d_perm;
+    CK(cudaMemcpyAsync(d_off.need(n + 1), offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    d_keys.need(n_pad);
+    k_sort_keys_init<<<(n_pad + 255) / 256, 256, 0, st>>>(d_off.p, n, n_pad, d_keys.p);
+    int launches = 2;
+    for (uint32_t size = 2; size <= n_pad; size <<= 1) {
+        uint32_t stride = size >> 1;
+        for (; stride >= 1024; stride >>= 1, ++launches)
+            k_bitonic_step<<<(n_pad / 2 + 255) / 256, 256, 0, st>>>(d_keys.p, n_pad, size, stride);
+        k_bitonic_local<<<n_pad / 2048, 1024, 0, st>>>(d_keys.p, size, stride);
+        ++launches;
+    }
+    k_sort_keys_perm<<<(n + 255) / 256, 256, 0, st>>>(d_keys.p, n, d_perm.need(n));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(perm, d_perm.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->stats.kernel_launches += launches;
+    ctx->stats.h2d_bytes += (int64_t)(n + 1) * 8;
+    ctx->stats.d2h_bytes += (int64_t)n * 4;
 }
 
 // ------------------------------------------------------------------------------------------------ extraction
@@ -158,7 +199,7 @@ void cluster_extract(rtl_ctx *ctx, int k, int both) {
         if (S.h_len[i] <= k || S.h_len[i] <= 6) throw InputError("read shorter than or equal to kmer size (kmer.cpp:9)");
     cudaStream_t st = ctx->stream;
     S.flags.need(4);
-    CK(cudaMemsetAsync(S.flags.p, 0, 4 * sizeof(int), st));
+    k_clear_keep_pack_flag<<<1, 1, 0, st>>>(S.flags.p, S.pack_flag.p);  // what k_pack_bases saw at upload time -> flags[0]
     S.d_len.need(n);
     CK(cudaMemcpyAsync(S.d_len.p, S.h_len.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     ctx->stats.h2d_bytes += (int64_t)n * 4;
@@ -207,7 +248,7 @@ void cluster_extract(rtl_ctx *ctx, int k, int both) {
         const int threads = n_pad <= 2048 ? 256 : (n_pad <= 4096 ? 512 : 1024);
         // gridDim.x limit is 2^31-1; y = strand
         dim3 grid((unsigned)cnt, both ? 2 : 1);
-        k_extract_smem<<<grid, threads, smem, st>>>(S.d_bases.p, S.d_off.p, S.read_list.p + start[c], k, n_pad,
+        k_extract_smem<<<grid, threads, smem, st>>>(S.d_pk.p, S.d_off.p, S.read_list.p + start[c], k, n_pad,
                                                     S.kh[0].p, S.kp[0].p, S.kh[1].p, S.kp[1].p, S.bv[0], S.bv[1],
                                                     S.bv_stride, S.pc.p, S.flags.p);
         CK(cudaGetLastError());
@@ -231,7 +272,7 @@ void cluster_extract(rtl_ctx *ctx, int k, int both) {
             S.long_scratch.need(at);
             CK(cudaMemcpyAsync(S.long_off.p, so.data(), cnt * 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
             dim3 grid((unsigned)cnt, both ? 2 : 1);
-            k_extract_long<<<grid, 1024, 0, st>>>(S.d_bases.p, S.d_off.p, S.read_list.p + start[n_cls], S.long_off.p,
+            k_extract_long<<<grid, 1024, 0, st>>>(S.d_pk.p, S.d_off.p, S.read_list.p + start[n_cls], S.long_off.p,
                                                   S.long_scratch.p, k, S.kh[0].p, S.kp[0].p, S.kh[1].p, S.kp[1].p,
                                                   S.bv[0], S.bv[1], S.bv_stride, S.pc.p, S.flags.p);
             CK(cudaGetLastError());

@@ -33,10 +33,42 @@ __device__ __forceinline__ int base_code(uint8_t c) {
     return ok ? ((c >> 1) & 3) : -1;
 }
 
+// ------------------------------------------------------------------------------------------------ K1: 2-bit packing
+// The read set on the device is 2-bit packed (kmer.hpp:25-31 codes, 16 bases per 32-bit word, base i of a word in bits
+// 2i..2i+1); every read starts on a word: read r's words start at pk_start(off, r).  The ASCII copy is only staging for this
+// kernel; k-mer extraction reads a quarter of the bytes, coalesced.  A base outside A,C,G,T,U raises the input flag.
+__host__ __device__ __forceinline__ uint64_t pk_start(const uint64_t *off, uint32_t r) { return (off[r] >> 4) + r; }
+__global__ void __launch_bounds__(256) k_pack_bases(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ off, uint32_t n,
+                                                    uint32_t *__restrict__ pk, int *err) {
+    // one warp per read at a time; a lane packs one word (16 bases read as one 16-byte load when aligned)
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    bool bad = false;
+    for (uint32_t r = warp; r < n; r += n_warps) {
+        const uint64_t o = off[r];
+        const int len = (int)(off[r + 1] - o);
+        const uint64_t w0 = pk_start(off, r);
+        for (int w = lane; w * 16 < len; w += 32) {
+            uint32_t word = 0;
+            const int m = min(16, len - w * 16);
+            for (int i = 0; i < m; ++i) {
+                const int c = base_code(bases[o + (uint64_t)w * 16 + i]);
+                if (c < 0) bad = true;
+                word |= (uint32_t)(c & 3) << (2 * i);
+            }
+            pk[w0 + w] = word;
+        }
+    }
+    if (bad) atomicExch(err, 2);
+}
+__device__ __forceinline__ int pk_code(const uint32_t *__restrict__ pk, uint64_t w0, int p) {
+    return (int)((pk[w0 + (uint32_t)(p >> 4)] >> (2 * (p & 15))) & 3u);
+}
+
 // ------------------------------------------------------------------------------------------------ K2: extraction
 // One CTA per (read, strand).  Keys (hash<<32 | pos) are bitonic-sorted in shared memory.
 // smem: keys[n_pad] u64 | bvw[128] u32 | codes[n_pad+32] u8
-__global__ void k_extract_smem(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ off,
+__global__ void k_extract_smem(const uint32_t *__restrict__ pk, const uint64_t *__restrict__ off,
                                const uint32_t *__restrict__ read_list, int k, int n_pad, uint32_t *kh_f, int32_t *kp_f,
                                uint32_t *kh_r, int32_t *kp_r, uint64_t *bv_f, uint64_t *bv_r, int bv_stride, int32_t *pc, int *err) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -50,14 +82,17 @@ __global__ void k_extract_smem(const uint8_t *__restrict__ bases, const uint64_t
     const int n = len - k;
     const int tid = threadIdx.x, nt = blockDim.x;
 
-    for (int p = tid; p < len; p += nt) {
-        int c = strand == 0 ? base_code(bases[o + p]) : base_code(bases[o + (len - 1 - p)]);
-        if (c < 0) {
-            atomicExch(err, 2);
-            c = 0;
-        } else if (strand)
-            c ^= 2;  // complement: A<->T, C<->G  (utils.cpp:15-24)
-        codes[p] = (uint8_t)c;
+    (void)err;
+    const uint64_t w0 = pk_start(off, r);
+    for (int w = tid; w * 16 < len; w += nt) {  // one packed word = 16 bases per thread and step
+        const uint32_t word = pk[w0 + w];
+        const int m = min(16, len - w * 16);
+        for (int i = 0; i < m; ++i) {
+            const int p = w * 16 + i;
+            const int c = (int)((word >> (2 * i)) & 3u);
+            if (strand == 0) codes[p] = (uint8_t)c;
+            else codes[len - 1 - p] = (uint8_t)(c ^ 2);  // reverse complement: A<->T, C<->G  (utils.cpp:15-24)
+        }
     }
     if (tid < 128) bvw[tid] = 0;
     __syncthreads();
@@ -114,7 +149,7 @@ __global__ void k_extract_smem(const uint8_t *__restrict__ bases, const uint64_t
 }
 
 // Same, for reads whose key list does not fit shared memory: keys live in a global scratch segment.
-__global__ void k_extract_long(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ off,
+__global__ void k_extract_long(const uint32_t *__restrict__ pk, const uint64_t *__restrict__ off,
                                const uint32_t *__restrict__ read_list, const uint64_t *__restrict__ scratch_off,
                                uint64_t *scratch, int k, uint32_t *kh_f, int32_t *kp_f, uint32_t *kh_r, int32_t *kp_r,
                                uint64_t *bv_f, uint64_t *bv_r, int bv_stride, int32_t *pc, int *err) {
@@ -128,14 +163,9 @@ __global__ void k_extract_long(const uint8_t *__restrict__ bases, const uint64_t
     while (n_pad < n) n_pad <<= 1;
     uint64_t *keys = scratch + scratch_off[blockIdx.x * 2 + strand];
     const int tid = threadIdx.x, nt = blockDim.x;
-    auto code_at = [&](int p) -> int {
-        int c = strand == 0 ? base_code(bases[o + p]) : base_code(bases[o + (len - 1 - p)]);
-        if (c < 0) {
-            atomicExch(err, 2);
-            return 0;
-        }
-        return strand ? (c ^ 2) : c;
-    };
+    (void)err;
+    const uint64_t w0 = pk_start(off, r);
+    auto code_at = [&](int p) -> int { return strand == 0 ? pk_code(pk, w0, p) : (pk_code(pk, w0, len - 1 - p) ^ 2); };
     if (tid < 128) bvw[tid] = 0;
     __syncthreads();
     for (int p = tid; p < n_pad; p += nt) {
@@ -184,6 +214,55 @@ __global__ void k_extract_long(const uint8_t *__restrict__ bases, const uint64_t
         for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
         if (tid == 0) pc[r] = c;
     }
+}
+
+// K1, visitation order: sort_read_set (fasta.cpp:458-464) is a stable sort by length, longest first.  The keys
+// (2^32-1 - length) << 32 | index are unique, so a plain bitonic sort of them IS that stable order.
+__global__ void k_sort_keys_init(const uint64_t *__restrict__ off, uint32_t n, uint32_t n_pad, uint64_t *keys) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    keys[i] = i < n ? (((uint64_t)(0xffffffffu - (uint32_t)(off[i + 1] - off[i])) << 32) | i) : ~0ull;
+}
+__global__ void k_bitonic_step(uint64_t *keys, uint32_t n_pad, uint32_t size, uint32_t stride) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (n_pad >> 1)) return;
+    const uint32_t i = 2 * t - (t & (stride - 1)), j = i + stride;
+    const uint64_t a = keys[i], b = keys[j];
+    const bool asc = (i & size) == 0;
+    if ((a > b) == asc) {
+        keys[i] = b;
+        keys[j] = a;
+    }
+}
+// all steps of the network with stride < 1024 of one merge stage, inside shared memory (one CTA per 2048 keys)
+__global__ void __launch_bounds__(1024) k_bitonic_local(uint64_t *keys, uint32_t size, uint32_t first_stride) {
+    __shared__ uint64_t s[2048];
+    const uint32_t base = blockIdx.x * 2048u, tid = threadIdx.x;
+    s[tid] = keys[base + tid];
+    s[tid + 1024] = keys[base + tid + 1024];
+    for (uint32_t stride = first_stride; stride > 0; stride >>= 1) {
+        __syncthreads();
+        const uint32_t i = 2 * tid - (tid & (stride - 1)), j = i + stride;
+        const uint64_t a = s[i], b = s[j];
+        const bool asc = ((base + i) & size) == 0;
+        if ((a > b) == asc) {
+            s[i] = b;
+            s[j] = a;
+        }
+    }
+    __syncthreads();
+    keys[base + tid] = s[tid];
+    keys[base + tid + 1024] = s[tid + 1024];
+}
+__global__ void k_sort_keys_perm(const uint64_t *__restrict__ keys, uint32_t n, uint32_t *perm) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[i] = (uint32_t)keys[i];
+}
+
+// extraction prologue: clear the flags, carrying over "the upload met a base outside ACGTU" (k_pack_bases)
+__global__ void k_clear_keep_pack_flag(int *flags, const int *pack_flag) {
+    flags[0] = *pack_flag ? 2 : 0;
+    flags[1] = flags[2] = flags[3] = 0;
 }
 
 __global__ void k_lengths(const uint64_t *__restrict__ off, int32_t *len, uint32_t n, int k, int *err) {

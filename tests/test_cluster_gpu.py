@@ -362,3 +362,14 @@ def test_cluster_reads_batched_equals_per_gene_calls(ctx, orc, wave):
         single = ctx.cluster_reads(one.bases, one.offsets, is_rna=False, **kw)
         c0, c1 = int(seg_cl_off[s]), int(seg_cl_off[s + 1])
         assert single.n_clusters == c1 - c0 and np.array_equal(single.main_id, got.main_id[c0:c1])
+
+
+@pytest.mark.parametrize("n", [1, 5, 2047, 2049, 70000])
+def test_sort_reads_by_length_is_the_reference_visitation_order(ctx, n):
+    """rtl_sort_reads_by_length == sort_read_set (fasta.cpp:458-464): stable, longest first; many equal lengths"""
+    rng = np.random.default_rng(n)
+    lens = rng.integers(7, 60, size=n) if n < 70000 else rng.integers(150, 400, size=n)
+    offsets = np.zeros(n + 1, np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    got = ctx.sort_by_length(offsets)
+    assert np.array_equal(got, np.argsort(-lens.astype(np.int64), kind="stable").astype(np.uint32))
