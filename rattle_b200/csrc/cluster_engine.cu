@@ -74,7 +74,7 @@ struct ClusterState {
     DevBuf<uint64_t> long_off, long_scratch;
     // wave state
     DevBuf<uint8_t> taken, owner_rev, is_seed;
-    DevBuf<int32_t> owner, item_read, item_rid, item_seg, cand, seed_item, wave, shard_list;
+    DevBuf<int32_t> owner, item_read, item_rid, item_seg, seg_first, seg_cur, cand, seed_item, wave, shard_list;
     DevBuf<uint32_t> memo;      // known k-mer-test failures between representatives (cluster_kernels.cuh: Memo)
     uint32_t rid_dim = 0;       // 0 = memo off
     DevBuf<uint32_t> best, acc;
@@ -110,6 +110,7 @@ static void set_smem_attrs(ClusterState &S) {
     CK(cudaFuncSetAttribute(k_bv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CK(cudaFuncSetAttribute(k_join_count, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CK(cudaFuncSetAttribute(k_pair_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CK(cudaFuncSetAttribute(k_resolve_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
     S.smem_attr_set = true;
 }
 
@@ -434,8 +435,8 @@ static void ensure_work_buffers(rtl_ctx *ctx, ClusterState &S, int64_t M) {
 // Result: owner[j] = item index of the seed that took item j (owner[j]==j for seeds), owner_rev[j] = rev flag.
 // Batched clustering (h_item_seg != nullptr): the items are the concatenation of independent problems ("segments",
 // contiguous item ranges; main.cpp:281-324 clusters every gene's reads on their own).  Pairs only exist inside a segment
-// (the scan drops the others), so one pass over all items is every segment's greedy pass at once; phase B of a wave
-// only has to reach the end of the segment its last candidate lies in (h_item_seg_end[item] = first item behind it).
+// (the scan drops the others), so one pass over all items is every segment's greedy pass at once (see the windowed loop
+// below).
 static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const int32_t *h_item_rid, double thr, bool both,
                         double t_s, double t_v,
                         std::vector<int32_t> &owner, std::vector<uint8_t> &owner_rev,
@@ -488,6 +489,99 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
     CK(cudaMemsetAsync(S.flags.p, 0, 16, st));
     CK(cudaStreamSynchronize(st));  // `cut` is pageable host memory
 
+    if (h_item_seg) {
+        // ---- batched clustering: windows of W consecutive segments; every wave takes the first untaken item of each
+        // segment of the window — a seed by construction, so there is no candidate x candidate phase — and scores the
+        // seeds against the window's untaken items (the scan drops pairs of different segments).  A window is done when
+        // a wave finds no seed.  Work = seeds x segment sizes, as in the reference's per-gene loops (main.cpp:281-324).
+        (void)h_item_seg_end;
+        std::vector<int32_t> seg_first;
+        for (int i = 0; i < M; ++i)
+            if (i == 0 || h_item_seg[i] != h_item_seg[i - 1]) seg_first.push_back(i);
+        const int n_segs = (int)seg_first.size();
+        seg_first.push_back(M);
+        CK(cudaMemcpyAsync(S.seg_first.need(n_segs + 1), seg_first.data(), (size_t)(n_segs + 1) * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(S.seg_cur.need(n_segs + 1), seg_first.data(), (size_t)n_segs * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));  // seg_first is pageable host memory
+        ctx->stats.h2d_bytes += (int64_t)(2 * n_segs + 1) * 4;
+        const int64_t chunk = std::max<int64_t>(1024, ctx->task_cap / (2 * (int64_t)W));
+        int32_t *hw = S.h_wave.p;
+        int *hf = S.h_flags.p;
+        for (int w0 = 0; w0 < n_segs; w0 += W) {
+            const int w1 = std::min(n_segs, w0 + W);
+            const int x_lo = seg_first[w0], x_hi = seg_first[w1];
+            while (true) {
+                CK(cudaMemsetAsync(S.wave.p, 0, 16, st));
+                k_select_seg<<<(w1 - w0 + 255) / 256, 256, 0, st>>>(S.taken.p, S.seg_first.p + w0, S.seg_cur.p + w0, w1 - w0,
+                                                                    S.seed_item.p, S.wave.p, S.owner.p, S.owner_rev.p);
+                CK(cudaGetLastError());
+                ctx->stats.kernel_launches++;
+                for (int64_t c0 = x_lo; c0 < x_hi; c0 += chunk) {
+                    const int64_t c1 = std::min<int64_t>(x_hi, c0 + chunk);
+                    CK(cudaMemsetAsync(S.counters.p, 0, 3 * sizeof(unsigned long long), st));
+                    BvScanArgs a{};
+                    a.bv_f = S.bv[0];
+                    a.bv_r = S.bv[1];
+                    a.bv_stride = S.bv_stride;
+                    a.pc = S.pc.p;
+                    a.item_read = d_item_read;
+                    a.item_seg = d_item_seg;
+                    a.seed_item = S.seed_item.p;
+                    a.n_seeds_p = S.wave.p + 2;
+                    a.tgt_list = nullptr;
+                    a.t0 = (int32_t)c0;
+                    a.t1 = (int32_t)c1;
+                    a.taken = S.taken.p;
+                    a.cut = S.cut.p;
+                    a.both = both;
+                    a.order_check = 0;
+                    a.rank = 0;
+                    a.world = 1;
+                    a.ts_cap = BVS_TS;
+                    a.memo = memo;
+                    a.tasks = S.tasks.p;
+                    a.n_tasks = S.counters.p;
+                    a.task_cap = (int64_t)S.tasks.cap;
+                    a.ovf = S.flags.p + 1;
+                    a.pair_counter = S.counters.p + 3;
+                    S.ev.begin(EV_BV, st);
+                    launch_bv_scan(ctx, a, c1 - c0, W, st);
+                    S.ev.end(EV_BV, st);
+                    ctx->stats.kernel_launches++;
+                    ctx->stats.bv_launches++;
+                    TaskView tv{S.seed_item.p, nullptr, d_item_read, memo};
+                    Sink sink{};
+                    sink.mode = 2;
+                    sink.best = S.best.p;
+                    run_pair_kernels(ctx, S, tv, t_s, t_v, sink, nullptr);
+                }
+                k_apply<<<ctx->n_sm, 256, 0, st>>>(S.best.p, x_lo, x_hi, S.seed_item.p, S.taken.p, S.owner.p, S.owner_rev.p);
+                ctx->stats.kernel_launches++;
+                CK(cudaMemcpyAsync(hw, S.wave.p, 12, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(hf, S.flags.p, 16, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                ctx->stats.d2h_bytes += 28;
+                S.ev.collect();
+                ctx->stats.waves++;
+                if (hf[1]) {
+                    if (hf[1] == 3) throw CapacityError("match scratch exhausted: raise option scratch_mb");
+                    if (hf[1] == 4) throw CapacityError("a read pair has 2^31 or more common k-mer matches (not representable)");
+                    throw CapacityError("candidate-pair buffer exhausted: raise option task_cap");
+                }
+                if (hw[2] == 0) break;  // no untaken item left in the window
+            }
+        }
+        owner.resize(M);
+        owner_rev.resize(M);
+        CK(cudaMemcpyAsync(owner.data(), S.owner.p, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(owner_rev.data(), S.owner_rev.p, M, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(S.h_counters.p, S.counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->stats.d2h_bytes += (int64_t)M * 5;
+        ctx->stats.rounds++;
+        return;
+    }
+
     ReadView R = view(S);
     int lo = 0;  // host-known lower bound of the device cursor
     const int64_t chunk = std::max<int64_t>(1024, ctx->task_cap / (2 * (int64_t)W));
@@ -500,13 +594,7 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
         CK(cudaMemsetAsync(S.acc.p, 0xff, (size_t)W * W * 4, st));
         CK(cudaMemsetAsync(S.counters.p, 0, 3 * sizeof(unsigned long long), st));
         ctx->stats.kernel_launches += 2;
-        // batched: how far does phase B have to look?  (the cursor now stands behind the last candidate)
-        int b_hi = M;
-        if (h_item_seg_end) {
-            CK(cudaMemcpyAsync(hw, S.wave.p, 12, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            if (hw[1] >= W && hw[0] >= 1 && hw[0] <= M) b_hi = h_item_seg_end[hw[0] - 1];
-        }
+        const int b_hi = M;
         // ---- phase A: candidates x candidates
         {
             BvScanArgs a{};
@@ -548,8 +636,14 @@ static void greedy_pass(rtl_ctx *ctx, int M, const int32_t *h_item_read, const i
             run_pair_kernels(ctx, S, tv, t_s, t_v, sink, nullptr);
             if (ctx->world > 1 && ctx->allreduce(ctx->allreduce_user, S.acc.p, (int64_t)W * W) != 0)
                 throw CudaError("allreduce callback failed");
-            k_resolve<<<1, 32, 0, st>>>(S.acc.p, W, S.cand.p, S.wave.p, S.seed_item.p, S.is_seed.p, S.owner.p,
-                                        S.owner_rev.p);
+            if (W <= 1024 && (W & 31) == 0) {
+                const size_t smem = ((size_t)W * (W / 32) + W / 32) * 4;
+                k_resolve_cta<<<1, 1024, smem, st>>>(S.acc.p, W, S.cand.p, S.wave.p, S.seed_item.p, S.is_seed.p, S.owner.p,
+                                                     S.owner_rev.p);
+            } else {
+                k_resolve<<<1, 32, 0, st>>>(S.acc.p, W, S.cand.p, S.wave.p, S.seed_item.p, S.is_seed.p, S.owner.p,
+                                            S.owner_rev.p);
+            }
             ctx->stats.kernel_launches++;
         }
         // ---- phase B: seeds x every later untaken item (items below the cursor are all taken)

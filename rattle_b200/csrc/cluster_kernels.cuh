@@ -1121,6 +1121,73 @@ __global__ void k_select(uint8_t *taken, int M, int W, int32_t *cand, int32_t *w
 }
 
 // mark candidates taken (after k_select so that the scan above reads a consistent state)
+// The same resolution for W <= 1024 by a whole CTA: the W x W decision matrix is read once, coalesced, by all warps and
+// turned into per-candidate bit masks "earlier candidates that match me" in shared memory (the matrix is sparse: one
+// shared atomicOr per match); warp 0 then walks the candidates in order with the mask of seeds so far in shared memory —
+// one AND + ballot per candidate instead of a strided global-memory scan (0.7 ms -> a few tens of microseconds per wave).
+// dynamic shared memory: W * (W / 32) + W / 32 words.
+__global__ void __launch_bounds__(1024) k_resolve_cta(const uint32_t *__restrict__ acc, int W, const int32_t *__restrict__ cand,
+                                                     int32_t *wave, int32_t *seed_item, uint8_t *is_seed, int32_t *owner,
+                                                     uint8_t *owner_rev) {
+    extern __shared__ uint32_t sm_res[];
+    const int WW = W >> 5;               // mask words per candidate (W is a multiple of 32 here)
+    uint32_t *hit = sm_res;              // [W][WW]: bit a of hit[b] = candidate a < b matches b
+    uint32_t *seeds = sm_res + (size_t)W * WW;  // [WW]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+    const int nc = wave[1];
+    for (int i = tid; i < W * WW + WW; i += blockDim.x) sm_res[i] = 0u;
+    __syncthreads();
+    for (int a = warp; a < nc; a += n_warps)
+        for (int b = (a + 1 - ((a + 1) & 31)) + lane; b < nc; b += 32)  // b > a, row a read coalesced
+            if (b > a && acc[(size_t)a * W + b] != 0xffffffffu) atomicOr(&hit[(size_t)b * WW + (a >> 5)], 1u << (a & 31));
+    __syncthreads();
+    if (warp != 0) return;
+    int ns = 0;
+    for (int b = 0; b < nc; ++b) {
+        uint32_t m = 0u;
+        if (lane < WW) m = hit[(size_t)b * WW + lane] & seeds[lane];
+        const unsigned any = __ballot_sync(0xffffffffu, m != 0u);
+        int found = -1;
+        if (any) {
+            const int wl = __ffs(any) - 1;
+            const uint32_t mw = __shfl_sync(0xffffffffu, m, wl);
+            found = wl * 32 + __ffs(mw) - 1;
+        }
+        if (lane == 0) {
+            if (found >= 0) {
+                is_seed[b] = 0;
+                owner[cand[b]] = cand[found];
+                owner_rev[cand[b]] = (uint8_t)acc[(size_t)found * W + b];
+            } else {
+                is_seed[b] = 1;
+                seed_item[ns] = cand[b];
+                seeds[b >> 5] |= 1u << (b & 31);
+            }
+        }
+        if (found < 0) ++ns;
+        __syncwarp();
+    }
+    if (lane == 0) wave[2] = ns;
+}
+// Batched clustering: the first untaken item of a segment has no earlier untaken item it could join, so it IS a seed.  One
+// thread per segment of the window picks it (seg_cur remembers where the segment's search stands), marks it taken and
+// appends it to the wave's seeds; their order does not matter (an item only ever matches the seed of its own segment).
+__global__ void k_select_seg(uint8_t *taken, const int32_t *__restrict__ seg_first, int32_t *seg_cur, int n_seg,
+                             int32_t *seed_item, int32_t *wave, int32_t *owner, uint8_t *owner_rev) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    int i = seg_cur[s];
+    const int end = seg_first[s + 1];
+    while (i < end && taken[i]) ++i;
+    if (i < end) {
+        taken[i] = 1;
+        owner[i] = i;
+        owner_rev[i] = 0;
+        seed_item[atomicAdd(&wave[2], 1)] = i;
+        ++i;
+    }
+    seg_cur[s] = i;
+}
 __global__ void k_mark_cand(uint8_t *taken, const int32_t *cand, const int32_t *wave, int32_t *owner, uint8_t *owner_rev) {
     const int nc = wave[1];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
