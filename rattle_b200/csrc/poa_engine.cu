@@ -849,7 +849,11 @@ static ChainSizes chain_sizes(const rtl_ctx *ctx, const PoaTask *t) {
         z.maxlen = std::max(z.maxlen, l);
         z.total += l;
     }
-    const long long cn = std::max<long long>(16, std::min<long long>(z.total + 8, 4ll * z.maxlen + 1024) * ctx->poa_mirror_pct / 100);
+    // graph nodes: at most one per base; in practice the longest read plus what every further read adds (its share of new
+    // bases: errors and isoform differences): 2.9-3.5 k nodes for 50 x 1.5 kb reads at 7 % error, ~7.7 k for 100 at 10 %.
+    // The slot allows (2 + reads/25) x the longest read (50 reads: 4 x, as measured above with 2 x headroom)
+    const double per_len = std::max(3.0, std::min(12.0, 2.0 + (double)t->len.size() / 25.0));
+    const long long cn = std::max<long long>(16, std::min<long long>(z.total + 8, (long long)(per_len * z.maxlen) + 1024) * ctx->poa_mirror_pct / 100);
     z.cap_n = (int)cn;
     z.cap_e = (int)(3 * cn);
     z.cap_a = (int)(4 * cn);
