@@ -857,7 +857,11 @@ static ChainSizes chain_sizes(const rtl_ctx *ctx, const PoaTask *t) {
     z.cap_n = (int)cn;
     z.cap_e = (int)(3 * cn);
     z.cap_a = (int)(4 * cn);
-    z.spill_cap = (int)std::min<long long>(65000, cn / 8 + 16);
+    // rows that some later row needs from beyond the ring: 1 % of the rows of a 50-read pack, but packs of 100+ noisy reads
+    // are bushier (an eighth of the rows was not enough for 45 of 50 such packs): the share grows with the read count
+    const size_t nr = t->len.size();
+    const double spill_share = nr <= 50 ? 0.125 : std::min(0.5, 0.125 + (double)(nr - 50) / 200.0);
+    z.spill_cap = (int)std::min<long long>(65000, (long long)(cn * spill_share) + 16);
     z.max_nst = (z.maxlen + PS_STRIP - 1) / PS_STRIP;
     z.hf_words = (ps_hf_words(z.cap_n, z.max_nst, z.spill_cap) + 63) & ~(size_t)63;
     z.code_words = (ps_code_words(z.cap_n, z.max_nst) + 63) & ~(size_t)63;
@@ -1306,6 +1310,7 @@ static void vote_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vector<
     // ---- round 1: vote
     const double tv0 = now_ms();
     std::vector<VoteRound1> r1(np);
+    int r1_chain[4] = {0, 0, 0, 0}, r1_vote[3] = {0, 0, 0};  // (RTL_TRACE: why packs leave the device pipeline)
     size_t n_rows = 0, n_cols = 0;
     int max_ncol = 1;
     {
@@ -1319,6 +1324,7 @@ static void vote_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vector<
             DVPack &V = vp[i];
             memset(&V, 0, sizeof(V));
             const bool ok = hp[i].status == DC_OK;
+            r1_chain[std::min(3, std::max(0, (int)hp[i].status))]++;
             V.msa_off = hmo[i];
             V.out_off = hmo[i];
             V.col_off = n_cols;
@@ -1426,6 +1432,8 @@ static void vote_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vector<
         std::stable_sort(r1[i].order.begin(), r1[i].order.end(),
                          [&](int a, int b) { return K.cseq[a].size() > K.cseq[b].size(); });
     });
+    for (size_t i = 0; i < np; ++i)
+        if (S.ch_packs.p[i].status == DC_OK) r1_vote[std::min(2, std::max(0, (int)vp[i].status))]++;
     const double tv2 = now_ms();
     // ---- round 2: chains on the corrected reads (device to device), in sub-batches that fit the arena
     std::vector<size_t> todo;
@@ -1536,9 +1544,14 @@ static void vote_batch(rtl_ctx *ctx, PoaState &P, PoaSlot &S, const std::vector<
             K.done = true;
         }
     }
-    if (getenv("RTL_TRACE"))
-        fprintf(stderr, "[rtl] device vote unit %d: %zu packs, round-1 vote kernels + D2H %.1f ms, host strings %.1f ms, round 2 %.1f ms\n",
-                (int)(&S - P.slot_store), np, tv1 - tv0, tv2 - tv1, now_ms() - tv2);
+    if (getenv("RTL_TRACE")) {
+        size_t n_done = 0;
+        for (auto *k : packs) n_done += k->done;
+        fprintf(stderr, "[rtl] device vote unit %d: %zu packs (%zu done; round-1 chain status ok/cap/degree/spill %d/%d/%d/%d, round-1 vote "
+                "ok/degenerate/letter %d/%d/%d), round-1 vote kernels + D2H %.1f ms, host strings %.1f ms, round 2 %.1f ms\n",
+                (int)(&S - P.slot_store), np, n_done, r1_chain[0], r1_chain[1], r1_chain[2], r1_chain[3], r1_vote[0], r1_vote[1], r1_vote[2],
+                tv1 - tv0, tv2 - tv1, now_ms() - tv2);
+    }
 }
 
 void poa_correct_unit(rtl_ctx *ctx, int unit, std::vector<VotePack *> &packs, double min_occ, double gap_occ, int n_threads) {
