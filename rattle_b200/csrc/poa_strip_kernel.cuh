@@ -137,11 +137,9 @@ __device__ __forceinline__ uint4 ps_lds128(uint32_t addr) {
 }
 
 __device__ __forceinline__ void ps_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void ps_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 #else  // CUDA_EMU: "shared-space addresses" are plain pointers
 inline void ps_prefetch_l2(const void *) {}
-inline void ps_prefetch_l1(const void *) {}
 using ps_saddr = uintptr_t;
 #define PS_DYNAMIC_SHARED(type, name) type *name = reinterpret_cast<type *>(emu::g_smem)
 inline unsigned long long ps_lds64(ps_saddr a) { return __atomic_load_n(reinterpret_cast<unsigned long long *>(a), __ATOMIC_SEQ_CST); }
@@ -462,19 +460,6 @@ __device__ __forceinline__ void ps_align_job(const PoaSJob &J, const uint8_t *__
                         bestv = m;
                         bestr = r;
                         *reinterpret_cast<uint4 *>(mine) = make_uint4(H[0], H[1], H[2], H[3]);
-                    }
-                    // ---- the NEXT row's predecessors that lie beyond the ring (spilled rows in HBM): their record is already
-                    // here, so the lines are requested a row ahead instead of stalling the fold on them
-                    if (((rc.y | rc.z | rc.w) & PS_FAR) != 0u && r < n) {
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            const uint32_t pw = q == 0 ? rc.y : (q == 1 ? rc.z : rc.w);
-                            if (pw & PS_FAR) {
-                                const uint32_t *g = hf + (hfs_o + (pw & 0xffffu) * hf_stride);
-                                ps_prefetch_l1(g);
-                                ps_prefetch_l1(g + 128);
-                            }
-                        }
                     }
                     __syncwarp();  // ring entry of row r complete before the next row's reads
                 }
