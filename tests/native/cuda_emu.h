@@ -139,6 +139,7 @@ inline unsigned atomicCAS(unsigned *p, unsigned expected, unsigned desired) {
     return expected;  // the value found
 }
 inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 
 // shared memory: the dynamic part is one host buffer (emu::g_smem), `__shared__` statics are function statics (one CTA
 // runs at a time); "shared-space addresses" are plain pointers (poa_strip_kernel.cuh: ps_saddr)
