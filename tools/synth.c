@@ -177,3 +177,12 @@ void synth_free(synth_t *S) {
     free(S->truth_rev);
     free(S);
 }
+
+/* ReadSet.take: reads idx[0..n) of (src, src_off) copied back to back into dst (dst_off = their new offsets, n+1
+ * entries, computed by the caller); one memcpy per read instead of one index per base */
+void synth_take(const char *src, const uint64_t *src_off, const int64_t *idx, uint64_t n, const uint64_t *dst_off, char *dst) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t a = src_off[idx[i]], b = src_off[idx[i] + 1];
+        memcpy(dst + dst_off[i], src + a, b - a);
+    }
+}

@@ -42,6 +42,9 @@ def _load():
         lib.synth_copy.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 5
         lib.synth_free.restype = None
         lib.synth_free.argtypes = [ctypes.c_void_p]
+        lib.synth_take.restype = None
+        lib.synth_take.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p,
+                                   ctypes.c_void_p]
         _lib = lib
     return _lib
 
@@ -73,11 +76,17 @@ class ReadSet:
         lens = self.lengths()[idx]
         offs = np.zeros(len(idx) + 1, dtype=np.uint64)
         offs[1:] = np.cumsum(lens)
-        src_start = self.offsets.astype(np.int64)[idx]
-        # gather via a flat index built from run starts
-        total = int(offs[-1])
-        flat = np.repeat(src_start - offs[:-1].astype(np.int64), lens) + np.arange(total, dtype=np.int64)
-        return ReadSet(self.bases[flat], offs, None if self.quals is None else self.quals[flat],
+        # one memcpy per read (tools/synth.c): an index per base would take 12 GB for a million 1.5-kb reads
+        lib = _load()
+        idx = np.ascontiguousarray(idx)
+        src_off = np.ascontiguousarray(self.offsets, dtype=np.uint64)
+
+        def gather(a):
+            a = np.ascontiguousarray(a)
+            out = np.empty(int(offs[-1]), dtype=a.dtype)
+            lib.synth_take(a.ctypes.data, src_off.ctypes.data, idx.ctypes.data, len(idx), offs.ctypes.data, out.ctypes.data)
+            return out
+        return ReadSet(gather(self.bases), offs, None if self.quals is None else gather(self.quals),
                        None if self.truth_tx is None else self.truth_tx[idx],
                        None if self.truth_rev is None else self.truth_rev[idx])
 
