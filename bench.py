@@ -150,13 +150,13 @@ def golden_form_digests(out):
 def ref_sample_genes(args, steps=None):
     """bounded CPU sample of the reference arm: the whole (warmup + steps) run has to end within a few minutes, so one
     step gets min(20 s, 300 s / (warmup + steps)) of reference work; measured on the bench box: 0.75 genes (x 50
-    reads) per core and second (correct dominates at these sizes and is linear in reads, clustering ~quadratic)"""
+    reads) per core and second, 0.6 taken for margin (correct dominates at these sizes and is linear in reads, clustering ~quadratic)"""
     if args.ref_genes > 0:
         return args.ref_genes
     cores = os.cpu_count() or 1
     n = max(1, steps if steps is not None else args.warmup + args.steps)
     per_step_s = min(20.0, 300.0 / n)
-    return int(min(2000, max(40, 0.75 * cores * per_step_s)))
+    return int(min(2000, max(40, 0.6 * cores * per_step_s)))
 
 
 def reference_arm(args, rank, world):
